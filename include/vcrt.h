@@ -1,0 +1,155 @@
+/*
+ * vcrt.h -- C ABI of the B200-native replacement for the reference's one hot path:
+ * the per-pixel path-tracing compute shader resources/shaders/source/ray-trace-compute.comp
+ * (and its -simple variant) of grigoryoskin/vulkan-compute-ray-tracing.
+ *
+ * Everything a host needs in order to do what src/main.cpp does with
+ * mcvkp::ComputeMaterial / mcvkp::ComputeModel is here: plain pointers and sizes, no C++,
+ * no torch types.  Each entry point cites the reference interface it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Error convention (replaces `throw std::runtime_error("failed to ...")`,
+ * ComputeMaterial.cpp:35-38, Buffer.h:71-79): every call returns VCRT_OK (0) or a negative
+ * code and never throws; the message is available from vcrt_last_error().
+ *
+ * Threading (reference: one host thread, one queue, main.cpp:323-395): one ctx = one device +
+ * one CUDA stream.  Calls on one ctx must not race; different ctxs are independent.
+ */
+#ifndef VCRT_H
+#define VCRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Data ABI: bit-identical to GpuModel::* (src/ray-tracing/GpuModels.h:18-63) and to the std430
+ * mirrors in resources/shaders/source/include/definitions.glsl:1-29.
+ * ---------------------------------------------------------------------------------------- */
+enum { VCRT_MAT_LIGHT = 0, VCRT_MAT_LAMBERTIAN = 1, VCRT_MAT_METAL = 2, VCRT_MAT_GLASS = 3 }; /* GpuModels.h:18-24 */
+
+typedef struct { uint32_t type; uint32_t _pad0[3]; float albedo[3]; uint32_t _pad1; } vcrt_material;        /* 32 B, GpuModels.h:26-30 */
+typedef struct { float v0[3]; uint32_t _pad0; float v1[3]; uint32_t _pad1; float v2[3]; uint32_t materialIndex; } vcrt_triangle; /* 48 B, :32-38 */
+typedef struct { float s[4]; uint32_t materialIndex; uint32_t _pad[3]; } vcrt_sphere;                        /* 32 B, :40-44 */
+typedef struct { float min[3]; uint32_t _pad0; float max[3]; int32_t leftNodeIndex; int32_t rightNodeIndex;
+                 int32_t objectIndex; uint32_t _pad1[2]; } vcrt_bvh_node;                                    /* 48 B, :47-54 */
+typedef struct { uint32_t triangleIndex; float area; } vcrt_light;                                            /* 8 B,  :57-63 */
+/* std140 uniform block, ray-trace-compute.comp:8-15 == UniformBufferObject, main.cpp:39-47 */
+typedef struct { float camPos[3]; float time; uint32_t currentSample; uint32_t numTriangles; uint32_t numLights; uint32_t numSpheres; } vcrt_ubo; /* 32 B */
+
+/* Descriptor bindings of the shader (ray-trace-compute.comp:8-39; order built by main.cpp:145-152) */
+enum {
+    VCRT_BINDING_UBO = 0, VCRT_BINDING_TARGET = 1, VCRT_BINDING_ACCUM = 2, VCRT_BINDING_TRIANGLES = 3,
+    VCRT_BINDING_MATERIALS = 4, VCRT_BINDING_BVH = 5, VCRT_BINDING_LIGHTS = 6, VCRT_BINDING_SPHERES = 7
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Render parameters: the reference's compile-time constants turned into run-time fields.
+ * Zero means "the shader's own value".
+ * ---------------------------------------------------------------------------------------- */
+enum { VCRT_SHADER_FULL = 0,    /* ray-trace-compute.comp        (main.cpp:144) */
+       VCRT_SHADER_SIMPLE = 1   /* ray-trace-compute-simple.comp (main.cpp:143) */ };
+enum { VCRT_TRAVERSAL_REFERENCE = 0, /* hit_bvh exactly as written (ray-trace-compute.comp:263-311), on the bound bvh[] */
+       VCRT_TRAVERSAL_FAST = 1,      /* same closest hit (same tie rule), repacked nodes, ordered + t-culled, persistent warps */
+       VCRT_TRAVERSAL_BRUTE_FORCE = 2/* hit_scene (:222-247): all triangles, then all spheres; the only mode that sees spheres */ };
+enum { VCRT_RNG_PCG_REF = 0,    /* random.glsl:4-22, seed (600*x+y)*(sample+1) */
+       VCRT_RNG_PHILOX = 1      /* Philox4x32-10, key (pixel, seed), counter (sample, draw/4) */ };
+enum { VCRT_ACCUM_RGBA8_REF = 0,/* running mean through the rgba8 target/accumulation pair (ray-trace-compute.comp:375-379 + main.cpp:253-261) */
+       VCRT_ACCUM_F32 = 1       /* sum of unclamped samples into an RGBA f32 buffer (A counts samples) */ };
+enum { VCRT_TRIG_LIBM = 0,      /* platform sinf/cosf (glibc on the CPU, CUDA libdevice on the GPU): ulp-level differences */
+       VCRT_TRIG_PORTABLE = 1   /* a fixed fp32 operation sequence shared by oracle and kernels: bit-exact across both */ };
+
+enum { VCRT_FLAG_REF_DISPATCH_COVERAGE = 1u, /* only floor(W/32)*32 x floor(H/32)*32 pixels, as main.cpp:228 dispatches */
+       VCRT_FLAG_WRITE_AOV = 2u,             /* primary-hit AOV (vcrt_aov per pixel) */
+       VCRT_FLAG_COUNT_TRAVERSAL = 4u        /* count node/triangle fetches (slower kernel variant) */ };
+
+typedef struct {
+    uint32_t struct_size;    /* = sizeof(vcrt_render_params) */
+    uint32_t shader;         /* VCRT_SHADER_* */
+    uint32_t traversal;      /* VCRT_TRAVERSAL_* */
+    uint32_t rng_mode;       /* VCRT_RNG_* */
+    uint32_t accum_mode;     /* VCRT_ACCUM_* */
+    uint32_t trig_mode;      /* VCRT_TRIG_* */
+    uint32_t max_bounces;    /* NUM_BOUNCES (:313 / simple :188); 0 = 2 (full) or 4 (simple) */
+    uint32_t stack_depth;    /* MAX_STACK_DEPTH (:262) of the reference traversal; 0 = 16; <= 64 */
+    uint32_t lights_length;  /* what lights.length() reports; 0 = element count of binding 6 */
+    uint32_t sample_begin;   /* first value of ubo.currentSample rendered by this call */
+    uint32_t sample_count;   /* samples per pixel rendered by this call; 0 = 1 */
+    uint32_t tile_rank;      /* image-tile sharding: 32x32 tile k (row-major) is rendered iff */
+    uint32_t tile_count;     /*   k % tile_count == tile_rank;  tile_count 0 or 1 = every tile */
+    uint32_t philox_seed;    /* VCRT_RNG_PHILOX key word 1 */
+    uint32_t flags;          /* VCRT_FLAG_* */
+    uint32_t _reserved;
+} vcrt_render_params;
+
+typedef struct { int32_t triangle; int32_t material; float t; uint32_t backFace; } vcrt_aov; /* triangle = -1 on a miss */
+
+typedef struct {
+    uint64_t rays;           /* closest-hit queries (primary + bounce) since the last reset */
+    uint64_t nodes;          /* BVH node records fetched   (only with VCRT_FLAG_COUNT_TRAVERSAL) */
+    uint64_t triangles;      /* triangle records fetched   (only with VCRT_FLAG_COUNT_TRAVERSAL) */
+    double   kernel_ms;      /* device time of the render kernels (CUDA events) since the last reset */
+    uint64_t launches;       /* kernels launched since the last reset */
+} vcrt_counters;
+
+enum { VCRT_OK = 0, VCRT_ERR_INVALID = -1, VCRT_ERR_CUDA = -2, VCRT_ERR_STATE = -3, VCRT_ERR_NOMEM = -4 };
+
+typedef struct vcrt_ctx vcrt_ctx;
+
+/* Context = device + stream + every device allocation.  Replaces VulkanApplicationContext bring-up
+ * (VulkanApplicationContext.cpp:47-119) + ComputeMaterial's pipeline/descriptor objects (ComputeMaterial.cpp:15-61). */
+int vcrt_create(int device, vcrt_ctx** out);
+int vcrt_destroy(vcrt_ctx* ctx);                     /* ~Material, Material.cpp:21-29; ~Buffer, Buffer.h:21-30 */
+const char* vcrt_last_error(const vcrt_ctx* ctx);    /* ctx may be NULL: error of the last failed vcrt_create on this thread */
+const char* vcrt_version(void);
+
+/* Selects the kernel by the reference's shader name ("ray-trace-compute" / "ray-trace-compute-simple", with or
+ * without directory and .spv/.comp suffix): the ComputeMaterial(computeShaderPath) argument, ComputeMaterial.cpp:9-13. */
+int vcrt_set_shader(vcrt_ctx* ctx, const char* shader_path);
+
+/* Storage buffers, bindings 3..7 (BufferUtils::createBundle<T> + addStorageBufferBundle, main.cpp:88-106, :148-152).
+ * `host` is copied; bytes must be a multiple of the record size.  Element counts come from byte sizes. */
+int vcrt_set_buffer(vcrt_ctx* ctx, int binding, const void* host, size_t bytes);
+/* Same, from a device pointer on ctx's device (copied device-to-device on ctx's stream). */
+int vcrt_set_buffer_device(vcrt_ctx* ctx, int binding, const void* dev, size_t bytes);
+
+/* Storage images, bindings 1 and 2: both rgba8 W x H (ImageUtils::createImage, main.cpp:108-140), zero-filled.
+ * Also (re)allocates the f32 accumulation buffer and the AOV buffer. */
+int vcrt_set_image_size(vcrt_ctx* ctx, uint32_t width, uint32_t height);
+
+/* The per-frame 32-byte uniform write (updateScene, main.cpp:166-183). */
+int vcrt_set_ubo(vcrt_ctx* ctx, const vcrt_ubo* ubo);
+
+/* ComputeModel::computeCommand(cmd, frame, x, y, z) == bind + vkCmdDispatch(x, y, z) (ComputeModel.cpp:21-25), followed
+ * by the target -> accumulation image copy the reference records right after it (main.cpp:253-261).  One sample
+ * (ubo.currentSample), reference traversal, reference RNG, rgba8 running mean, x*32 by y*32 pixels. Asynchronous. */
+int vcrt_dispatch(vcrt_ctx* ctx, uint32_t groups_x, uint32_t groups_y, uint32_t groups_z);
+
+/* The same path with the shader's compile-time constants as parameters and the sample loop inside the kernel.
+ * camPos is taken from the current UBO; ubo.currentSample is ignored (params.sample_begin is used). Asynchronous. */
+int vcrt_render(vcrt_ctx* ctx, const vcrt_render_params* params);
+
+int vcrt_clear_accum(vcrt_ctx* ctx);                                /* zero target, accumulation, f32 accumulation, AOV */
+int vcrt_resolve(vcrt_ctx* ctx, uint32_t total_samples, float gamma); /* f32 accumulation / total -> clamp -> pow(1/gamma) -> target rgba8 (gamma<=0: none; 2.2 = post-process-shader.frag:67-68) */
+
+/* Read-backs (synchronise ctx's stream).  bytes must equal the buffer size. */
+int vcrt_read_target_rgba8(vcrt_ctx* ctx, void* dst, size_t bytes); /* getStorageImages()[0], main.cpp:194 */
+int vcrt_read_accum_rgba8(vcrt_ctx* ctx, void* dst, size_t bytes);  /* getStorageImages()[1], main.cpp:195 */
+int vcrt_read_accum_f32(vcrt_ctx* ctx, void* dst, size_t bytes);    /* W*H*4 floats */
+int vcrt_read_aov(vcrt_ctx* ctx, void* dst, size_t bytes);          /* W*H vcrt_aov */
+int vcrt_write_accum_f32(vcrt_ctx* ctx, const void* src, size_t bytes); /* resume: reload a dumped accumulation */
+
+/* Device pointers of ctx-owned images, for collectives (NCCL) and zero-copy consumers. */
+int vcrt_device_ptr(vcrt_ctx* ctx, int what /* 0 target rgba8, 1 accum rgba8, 2 accum f32, 3 aov */, void** out, size_t* bytes);
+
+int vcrt_synchronize(vcrt_ctx* ctx);
+int vcrt_get_counters(vcrt_ctx* ctx, vcrt_counters* out);           /* synchronises */
+int vcrt_reset_counters(vcrt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCRT_H */

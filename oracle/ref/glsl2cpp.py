@@ -25,6 +25,9 @@ The rewrite is purely syntactic -- no arithmetic expression is changed:
       struct has the std430 layout the host uploads (checked by static_asserts in the driver)
   R10 the call `imageSize(` -> `imageSize_(` (main() declares a local of the same name, which
       in C++ would shadow the function inside its own initialiser)
+  R12 a `vecN(...)` constructor call whose arguments themselves call random() is brace-initialised
+      (`vecN{...}`): GLSL evaluates call arguments left to right (GLSL 4.50 spec, 6.1.1), C++ leaves the
+      order of `f(a(), b(), c())` unspecified (GCC goes right to left) but guarantees it for braces
   R11 optional overrides of `#define NUM_BOUNCES n` / `#define MAX_STACK_DEPTH n`
       (BASELINE configs need depth 4/8 and >16 stack for 1M-triangle trees; the verbatim
       variant keeps the shader's values)
@@ -42,6 +45,23 @@ def strip_comments(src):
     src = re.sub(r'/\*.*?\*/', lambda m: '\n' * m.group(0).count('\n'), src, flags=re.S)
     src = re.sub(r'//[^\n]*', '', src)
     return src
+
+
+def brace_random_ctor_args(src):
+    out, i = [], 0
+    for m in re.finditer(r'\bvec[234]\s*\(', src):
+        if m.start() < i:
+            continue
+        depth, j = 1, m.end()
+        while depth:
+            depth += {'(': 1, ')': -1}.get(src[j], 0)
+            j += 1
+        inner = src[m.end():j - 1]
+        if len(re.findall(r'\brandom\s*\(', inner)) >= 2:
+            out.append(src[i:m.end() - 1] + '{' + inner + '}')
+            i = j
+    out.append(src[i:])
+    return ''.join(out)
 
 
 def rewrite(src, src_dir, is_definitions=False, overrides=None):
@@ -75,6 +95,8 @@ def rewrite(src, src_dir, is_definitions=False, overrides=None):
     src = re.sub(r'\bimageSize\s*\(', 'imageSize_(', src)
     # R5 swizzles
     src = SWIZZLE.sub(r'.\1()', src)
+    # R12
+    src = brace_random_ctor_args(src)
     # R3 float literals (skip ones that already carry an f suffix: the look-ahead excludes \w)
     src = FLOAT_LIT.sub(r'\1f', src)
     # R11
