@@ -1,0 +1,368 @@
+// vcrt_api.cu -- the C ABI of include/vcrt.h: context, buffers, dispatch.  No CPU rendering path exists in
+// this library: every render call launches CUDA kernels or fails with an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vcrt.h"
+#include "vcrt_host_setup.h"
+#include "vcrt_launch.h"
+#include "vcrt_repack.h"
+
+using namespace vcrt;
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;      // bytes in use
+    size_t capacity = 0;
+};
+
+struct vcrt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int shader = VCRT_SHADER_FULL;
+    DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
+    std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
+    bool fast_dirty = true;
+    bool fast_ok = false;
+    std::string fast_err;
+    DevBuf fnodes, ftris;
+    int32_t froot = (int32_t)0x80000000;
+    uint32_t nfnodes = 0;
+    uint32_t W = 0, H = 0;
+    DevBuf target, accum8, accumf, aov;
+    vcrt_ubo ubo;
+    unsigned long long* d_counters = nullptr;   // rays, nodes, tris, work counter
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    double kernel_ms = 0.0;
+    uint64_t launches = 0;
+};
+
+static thread_local std::string g_create_error;
+
+static const size_t kStride[8] = {0, 0, 0, sizeof(vcrt_triangle), sizeof(vcrt_material), sizeof(vcrt_bvh_node), sizeof(vcrt_light), sizeof(vcrt_sphere)};
+
+static_assert(sizeof(vcrt_material) == 32 && sizeof(vcrt_triangle) == 48 && sizeof(vcrt_sphere) == 32 && sizeof(vcrt_bvh_node) == 48 &&
+              sizeof(vcrt_light) == 8 && sizeof(vcrt_ubo) == 32 && sizeof(vcrt_aov) == 16, "data ABI");
+static_assert(offsetof(vcrt_material, albedo) == 16 && offsetof(vcrt_triangle, v1) == 16 && offsetof(vcrt_triangle, v2) == 32 &&
+              offsetof(vcrt_triangle, materialIndex) == 44 && offsetof(vcrt_sphere, materialIndex) == 16 && offsetof(vcrt_bvh_node, max) == 16 &&
+              offsetof(vcrt_bvh_node, leftNodeIndex) == 28 && offsetof(vcrt_bvh_node, rightNodeIndex) == 32 && offsetof(vcrt_bvh_node, objectIndex) == 36,
+              "data ABI offsets (GpuModels.h:26-63)");
+
+static int fail(vcrt_ctx* c, int code, const std::string& msg) {
+    if (c) c->error = msg; else g_create_error = msg;
+    return code;
+}
+static int cuda_fail(vcrt_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, VCRT_ERR_CUDA, std::string("failed to ") + what + ": " + cudaGetErrorString(e));
+}
+#define CU(c, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, (what)); } while (0)
+
+static int ensure(vcrt_ctx* c, DevBuf& b, size_t bytes, const char* what) {
+    if (bytes > b.capacity) {
+        if (b.ptr) CU(c, cudaFree(b.ptr), "free device buffer");
+        b.ptr = nullptr; b.capacity = 0;
+        CU(c, cudaMalloc(&b.ptr, bytes ? bytes : 16), what);
+        b.capacity = bytes ? bytes : 16;
+    }
+    b.bytes = bytes;
+    return VCRT_OK;
+}
+
+extern "C" {
+
+const char* vcrt_version(void) { return "vcrt 0.1 (sm_100a)"; }
+
+const char* vcrt_last_error(const vcrt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int vcrt_create(int device, vcrt_ctx** out) {
+    if (!out) return fail(nullptr, VCRT_ERR_INVALID, "vcrt_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "enumerate CUDA devices");
+    if (device < 0 || device >= n) return fail(nullptr, VCRT_ERR_INVALID, "vcrt_create: no such CUDA device");
+    vcrt_ctx* c = new (std::nothrow) vcrt_ctx();
+    if (!c) return fail(nullptr, VCRT_ERR_NOMEM, "vcrt_create: out of host memory");
+    c->device = device;
+    std::memset(&c->ubo, 0, sizeof c->ubo);
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream)) != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "create context");
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return VCRT_OK;
+}
+
+int vcrt_destroy(vcrt_ctx* c) {
+    if (!c) return VCRT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
+    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov}) if (b->ptr) cudaFree(b->ptr);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return VCRT_OK;
+}
+
+int vcrt_set_shader(vcrt_ctx* c, const char* path) {
+    if (!c || !path) return fail(c, VCRT_ERR_INVALID, "vcrt_set_shader: NULL argument");
+    std::string s(path);
+    size_t slash = s.find_last_of("/\\");
+    if (slash != std::string::npos) s = s.substr(slash + 1);
+    size_t dot = s.find_last_of('.');
+    if (dot != std::string::npos) s = s.substr(0, dot);
+    if (s == "ray-trace-compute") c->shader = VCRT_SHADER_FULL;
+    else if (s == "ray-trace-compute-simple") c->shader = VCRT_SHADER_SIMPLE;
+    else return fail(c, VCRT_ERR_INVALID, "failed to open file: no kernel for shader '" + std::string(path) + "'");
+    return VCRT_OK;
+}
+
+static int set_buffer_common(vcrt_ctx* c, int binding, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (binding < VCRT_BINDING_TRIANGLES || binding > VCRT_BINDING_SPHERES) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: binding must be 3..7");
+    if (bytes % kStride[binding] != 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: size is not a multiple of the record size");
+    if (bytes / kStride[binding] > 0x7fffffffu) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: too many records");
+    if (bytes && !src) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: NULL source");
+    CU(c, cudaSetDevice(c->device), "set device");
+    int rc = ensure(c, c->ssbo[binding], bytes, "allocate storage buffer");
+    if (rc) return rc;
+    if (bytes) CU(c, cudaMemcpyAsync(c->ssbo[binding].ptr, src, bytes, kind, c->stream), "copy storage buffer");
+    if (binding == VCRT_BINDING_TRIANGLES || binding == VCRT_BINDING_BVH) {
+        std::vector<uint8_t>& shadow = binding == VCRT_BINDING_TRIANGLES ? c->host_tris : c->host_bvh;
+        shadow.resize(bytes);
+        if (bytes) {
+            if (kind == cudaMemcpyHostToDevice) std::memcpy(shadow.data(), src, bytes);
+            else {
+                CU(c, cudaMemcpyAsync(shadow.data(), src, bytes, cudaMemcpyDeviceToHost, c->stream), "read back storage buffer");
+                CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+            }
+        }
+        c->fast_dirty = true;
+    }
+    if (kind == cudaMemcpyHostToDevice) CU(c, cudaStreamSynchronize(c->stream), "synchronize");  // host pointer is borrowed for the call only
+    return VCRT_OK;
+}
+
+int vcrt_set_buffer(vcrt_ctx* c, int binding, const void* host, size_t bytes) { return set_buffer_common(c, binding, host, bytes, cudaMemcpyHostToDevice); }
+int vcrt_set_buffer_device(vcrt_ctx* c, int binding, const void* dev, size_t bytes) { return set_buffer_common(c, binding, dev, bytes, cudaMemcpyDeviceToDevice); }
+
+int vcrt_clear_accum(vcrt_ctx* c) {
+    if (!c) return VCRT_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device), "set device");
+    for (DevBuf* b : {&c->target, &c->accum8, &c->accumf, &c->aov})
+        if (b->ptr && b->bytes) CU(c, cudaMemsetAsync(b->ptr, 0, b->bytes, c->stream), "clear image");
+    return VCRT_OK;
+}
+
+int vcrt_set_image_size(vcrt_ctx* c, uint32_t w, uint32_t h) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (w == 0 || h == 0 || w > 65536u || h > 65536u) return fail(c, VCRT_ERR_INVALID, "vcrt_set_image_size: bad extent");
+    CU(c, cudaSetDevice(c->device), "set device");
+    const size_t npix = (size_t)w * h;
+    int rc;
+    if ((rc = ensure(c, c->target, npix * 4, "allocate target image")) || (rc = ensure(c, c->accum8, npix * 4, "allocate accumulation image")) ||
+        (rc = ensure(c, c->accumf, npix * 16, "allocate f32 accumulation")) || (rc = ensure(c, c->aov, npix * sizeof(vcrt_aov), "allocate AOV buffer")))
+        return rc;
+    c->W = w; c->H = h;
+    return vcrt_clear_accum(c);
+}
+
+int vcrt_set_ubo(vcrt_ctx* c, const vcrt_ubo* ubo) {
+    if (!c || !ubo) return fail(c, VCRT_ERR_INVALID, "vcrt_set_ubo: NULL argument");
+    c->ubo = *ubo;
+    return VCRT_OK;
+}
+
+static int prepare_fast(vcrt_ctx* c) {
+    if (c->fast_dirty) {
+        FastBvh fb;
+        c->fast_err.clear();
+        c->fast_ok = build_fast_bvh((const vcrt_bvh_node*)c->host_bvh.data(), (uint32_t)(c->host_bvh.size() / sizeof(vcrt_bvh_node)),
+                                    (const vcrt_triangle*)c->host_tris.data(), (uint32_t)(c->host_tris.size() / sizeof(vcrt_triangle)), fb, c->fast_err);
+        c->fast_dirty = false;
+        if (c->fast_ok) {
+            int rc;
+            if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris.size() * 4, "allocate repacked triangles"))) return rc;
+            if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
+            if (!fb.tris.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris.data(), fb.tris.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
+            CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+            c->froot = fb.root;
+            c->nfnodes = fb.num_nodes();
+        }
+    }
+    if (!c->fast_ok) return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err);
+    return VCRT_OK;
+}
+
+static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW, uint32_t covH) {
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "render: no storage images bound (vcrt_set_image_size)");
+    if (p.shader > VCRT_SHADER_SIMPLE || p.traversal > VCRT_TRAVERSAL_BRUTE_FORCE || p.rng_mode > VCRT_RNG_PHILOX || p.accum_mode > VCRT_ACCUM_F32 ||
+        p.trig_mode > VCRT_TRIG_PORTABLE)
+        return fail(c, VCRT_ERR_INVALID, "render: enum field out of range");
+    if (p.stack_depth > VCRT_MAX_STACK) return fail(c, VCRT_ERR_INVALID, "render: stack_depth > 64");
+    if (p.tile_count > 1 && p.tile_rank >= p.tile_count) return fail(c, VCRT_ERR_INVALID, "render: tile_rank >= tile_count");
+    CU(c, cudaSetDevice(c->device), "set device");
+
+    KernelArgs a;
+    std::memset(&a, 0, sizeof a);
+    SceneView& s = a.scene;
+    s.tris = (const float4*)c->ssbo[VCRT_BINDING_TRIANGLES].ptr;   s.ntris = (uint32_t)(c->ssbo[VCRT_BINDING_TRIANGLES].bytes / sizeof(vcrt_triangle));
+    s.mats = (const float4*)c->ssbo[VCRT_BINDING_MATERIALS].ptr;   s.nmats = (uint32_t)(c->ssbo[VCRT_BINDING_MATERIALS].bytes / sizeof(vcrt_material));
+    s.bvh = (const float4*)c->ssbo[VCRT_BINDING_BVH].ptr;          s.nbvh = (uint32_t)(c->ssbo[VCRT_BINDING_BVH].bytes / sizeof(vcrt_bvh_node));
+    s.lights = (const vcrt_light*)c->ssbo[VCRT_BINDING_LIGHTS].ptr; s.nlights = (uint32_t)(c->ssbo[VCRT_BINDING_LIGHTS].bytes / sizeof(vcrt_light));
+    s.spheres = (const float4*)c->ssbo[VCRT_BINDING_SPHERES].ptr;  s.nspheres = (uint32_t)(c->ssbo[VCRT_BINDING_SPHERES].bytes / sizeof(vcrt_sphere));
+    if (p.traversal == VCRT_TRAVERSAL_FAST) {
+        int rc = prepare_fast(c);
+        if (rc) return rc;
+        s.fnodes = (const float4*)c->fnodes.ptr; s.ftris = (const float4*)c->ftris.ptr; s.nfnodes = c->nfnodes; s.froot = c->froot;
+    } else {
+        s.froot = (int32_t)0x80000000;
+    }
+
+    setup_args(a, c->ubo, p, c->W, c->H, covW, covH, s.nlights);
+    a.target = (uchar4*)c->target.ptr; a.accum8 = (uchar4*)c->accum8.ptr; a.accumf = (float4*)c->accumf.ptr; a.aov = (vcrt_aov*)c->aov.ptr;
+    a.counters = c->d_counters;
+    a.work_counter = (unsigned int*)(c->d_counters + 3);
+
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0), "create event");
+    CU(c, cudaEventCreate(&e1), "create event");
+    CU(c, cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream), "reset work counter");
+    CU(c, cudaEventRecord(e0, c->stream), "record event");
+    const bool count = (p.flags & VCRT_FLAG_COUNT_TRAVERSAL) != 0;
+    cudaError_t e;
+    if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
+    else if (p.traversal == VCRT_TRAVERSAL_BRUTE_FORCE) e = launch_render_brute(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
+    else e = launch_render_reference(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
+    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, e, "launch render kernel"); }
+    CU(c, cudaEventRecord(e1, c->stream), "record event");
+    c->events.emplace_back(e0, e1);
+    c->launches += 1;
+    return VCRT_OK;
+}
+
+int vcrt_render(vcrt_ctx* c, const vcrt_render_params* p) {
+    if (!c || !p) return fail(c, VCRT_ERR_INVALID, "vcrt_render: NULL argument");
+    if (p->struct_size != sizeof(vcrt_render_params)) return fail(c, VCRT_ERR_INVALID, "vcrt_render: struct_size mismatch");
+    const bool ref_cov = (p->flags & VCRT_FLAG_REF_DISPATCH_COVERAGE) != 0;
+    return render_common(c, *p, ref_cov ? (c->W / 32) * 32 : c->W, ref_cov ? (c->H / 32) * 32 : c->H);
+}
+
+int vcrt_dispatch(vcrt_ctx* c, uint32_t gx, uint32_t gy, uint32_t gz) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (gz == 0 || gx == 0 || gy == 0) return VCRT_OK;   // vkCmdDispatch with a zero dimension does nothing
+    vcrt_render_params p;
+    std::memset(&p, 0, sizeof p);
+    p.struct_size = sizeof p;
+    p.shader = (uint32_t)c->shader;
+    p.traversal = VCRT_TRAVERSAL_REFERENCE;
+    p.rng_mode = VCRT_RNG_PCG_REF;
+    p.accum_mode = VCRT_ACCUM_RGBA8_REF;
+    p.trig_mode = VCRT_TRIG_LIBM;
+    p.sample_begin = c->ubo.currentSample;
+    p.sample_count = 1;
+    const uint64_t cw = (uint64_t)gx * 32u, ch = (uint64_t)gy * 32u;   // invocations beyond the image neither load nor store
+    return render_common(c, p, (uint32_t)(cw < c->W ? cw : c->W), (uint32_t)(ch < c->H ? ch : c->H));
+}
+
+int vcrt_resolve(vcrt_ctx* c, uint32_t total_samples, float gamma) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_resolve: no storage images bound");
+    if (total_samples == 0) return fail(c, VCRT_ERR_INVALID, "vcrt_resolve: total_samples is 0");
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, launch_resolve((const float4*)c->accumf.ptr, (uchar4*)c->target.ptr, c->W * c->H, 1.0f / (float)total_samples, gamma > 0.0f ? 1.0f / gamma : 0.0f, c->stream),
+       "launch resolve kernel");
+    c->launches += 1;
+    return VCRT_OK;
+}
+
+static int read_common(vcrt_ctx* c, const DevBuf& b, void* dst, size_t bytes, const char* what) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, std::string(what) + ": no storage images bound");
+    if (!dst || bytes != b.bytes) return fail(c, VCRT_ERR_INVALID, std::string(what) + ": size mismatch");
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, cudaMemcpyAsync(dst, b.ptr, bytes, cudaMemcpyDeviceToHost, c->stream), what);
+    CU(c, cudaStreamSynchronize(c->stream), what);
+    return VCRT_OK;
+}
+
+int vcrt_read_target_rgba8(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->target, dst, bytes, "read target image") : VCRT_ERR_INVALID; }
+int vcrt_read_accum_rgba8(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->accum8, dst, bytes, "read accumulation image") : VCRT_ERR_INVALID; }
+int vcrt_read_accum_f32(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->accumf, dst, bytes, "read f32 accumulation") : VCRT_ERR_INVALID; }
+int vcrt_read_aov(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->aov, dst, bytes, "read AOV buffer") : VCRT_ERR_INVALID; }
+
+int vcrt_write_accum_f32(vcrt_ctx* c, const void* src, size_t bytes) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_write_accum_f32: no storage images bound");
+    if (!src || bytes != c->accumf.bytes) return fail(c, VCRT_ERR_INVALID, "vcrt_write_accum_f32: size mismatch");
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, cudaMemcpyAsync(c->accumf.ptr, src, bytes, cudaMemcpyHostToDevice, c->stream), "write f32 accumulation");
+    CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+    return VCRT_OK;
+}
+
+int vcrt_device_ptr(vcrt_ctx* c, int what, void** out, size_t* bytes) {
+    if (!c || !out) return fail(c, VCRT_ERR_INVALID, "vcrt_device_ptr: NULL argument");
+    const DevBuf* b = what == 0 ? &c->target : what == 1 ? &c->accum8 : what == 2 ? &c->accumf : what == 3 ? &c->aov : nullptr;
+    if (!b) return fail(c, VCRT_ERR_INVALID, "vcrt_device_ptr: unknown buffer");
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_device_ptr: no storage images bound");
+    *out = b->ptr;
+    if (bytes) *bytes = b->bytes;
+    return VCRT_OK;
+}
+
+int vcrt_synchronize(vcrt_ctx* c) {
+    if (!c) return VCRT_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+    return VCRT_OK;
+}
+
+static int drain_events(vcrt_ctx* c) {
+    CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+    for (auto& ev : c->events) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) c->kernel_ms += ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    c->events.clear();
+    return VCRT_OK;
+}
+
+int vcrt_get_counters(vcrt_ctx* c, vcrt_counters* out) {
+    if (!c || !out) return fail(c, VCRT_ERR_INVALID, "vcrt_get_counters: NULL argument");
+    CU(c, cudaSetDevice(c->device), "set device");
+    int rc = drain_events(c);
+    if (rc) return rc;
+    unsigned long long h[3];
+    CU(c, cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost), "read counters");
+    out->rays = h[0]; out->nodes = h[1]; out->triangles = h[2];
+    out->kernel_ms = c->kernel_ms;
+    out->launches = c->launches;
+    return VCRT_OK;
+}
+
+int vcrt_reset_counters(vcrt_ctx* c) {
+    if (!c) return VCRT_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device), "set device");
+    int rc = drain_events(c);
+    if (rc) return rc;
+    CU(c, cudaMemset(c->d_counters, 0, 3 * sizeof(unsigned long long)), "reset counters");
+    c->kernel_ms = 0.0;
+    c->launches = 0;
+    return VCRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// vcrt_fast.cuh -- fast closest-hit traversal over records repacked from the bound bvh[] / triangles[].
+//
+// Same result as hit_bvh (ray-trace-compute.comp:263-311), by construction:
+//   * the accept/reject arithmetic of every triangle is tri_test -- the reference's operation order, no FMA;
+//   * the reference keeps the FIRST leaf in its fixed right-child-first DFS order among equal-t hits (strict
+//     `t < closest_so_far`); triangles are stored in exactly that order, so the slot index is the tie rank and
+//     `t == closest && slot < best` reproduces the rule under any visiting order;
+//   * boxes only cull.  The reference pads every box by 1e-4 (Bvh.h:16,94-98), orders of magnitude more than
+//     the rounding differences between its divide-based slab test and the fma slab test here, so both visit
+//     every leaf that holds an acceptable hit.  Culling with `tNear > closest` (strict) keeps equal-t leaves.
+//
+// Layout (built by vcrt_repack.cpp from the reference arrays, all records 16-byte aligned, 128-bit loads):
+//   inner node, 64 B:  {L.min.x L.max.x L.min.y L.max.y} {R.min.x R.max.x R.min.y R.max.y}
+//                      {L.min.z L.max.z R.min.z R.max.z} {childL childR - -}
+//                      child >= 0: inner node index;  child < 0: leaf, triangle slot = ~child;  empty: box (+inf,-inf)
+//   triangle, 48 B:    {v0.xyz, original index} {v1.xyz, materialIndex} {v2.xyz, -}   in reference DFS leaf order
+#pragma once
+
+#include "vcrt_core.cuh"
+
+namespace vcrt {
+
+#define VCRT_FAST_STACK 48
+#define VCRT_FAST_EMPTY ((int32_t)0x80000000)
+
+VCRT_HD float fmin_(float a, float b) { return fminf(a, b); }
+VCRT_HD float fmax_(float a, float b) { return fmaxf(a, b); }
+
+template <bool COUNT>
+VCRT_HD bool hit_bvh_fast(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
+    int32_t node = s.froot;
+    if (node == VCRT_FAST_EMPTY) return false;
+
+    // 1/d with a guard so that 0 * inf never appears; ood = o/d for the fma slab form
+    const float tiny = 1e-30f;
+    float3 idir = f3(1.0f / (fabsf(r.d.x) > tiny ? r.d.x : copysignf(tiny, r.d.x)),
+                     1.0f / (fabsf(r.d.y) > tiny ? r.d.y : copysignf(tiny, r.d.y)),
+                     1.0f / (fabsf(r.d.z) > tiny ? r.d.z : copysignf(tiny, r.d.z)));
+    float3 ood = f3(r.o.x * idir.x, r.o.y * idir.y, r.o.z * idir.z);
+
+    float closest = VCRT_T_MAX;
+    int32_t best = -1;
+    int32_t stack[VCRT_FAST_STACK];
+    int sp = 0;
+
+    for (;;) {
+        if (node >= 0) {
+            const float4* p = s.fnodes + 4 * (size_t)node;
+            const float4 n0 = ldg4(p), n1 = ldg4(p + 1), n2 = ldg4(p + 2), n3 = ldg4(p + 3);
+            if (COUNT) st.nodes++;
+            const float lx0 = fmaf(n0.x, idir.x, -ood.x), lx1 = fmaf(n0.y, idir.x, -ood.x);
+            const float ly0 = fmaf(n0.z, idir.y, -ood.y), ly1 = fmaf(n0.w, idir.y, -ood.y);
+            const float lz0 = fmaf(n2.x, idir.z, -ood.z), lz1 = fmaf(n2.y, idir.z, -ood.z);
+            const float rx0 = fmaf(n1.x, idir.x, -ood.x), rx1 = fmaf(n1.y, idir.x, -ood.x);
+            const float ry0 = fmaf(n1.z, idir.y, -ood.y), ry1 = fmaf(n1.w, idir.y, -ood.y);
+            const float rz0 = fmaf(n2.z, idir.z, -ood.z), rz1 = fmaf(n2.w, idir.z, -ood.z);
+            const float lN = fmax_(fmax_(fmin_(lx0, lx1), fmin_(ly0, ly1)), fmax_(fmin_(lz0, lz1), 0.0f));
+            const float lF = fmin_(fmin_(fmax_(lx0, lx1), fmax_(ly0, ly1)), fmax_(lz0, lz1)) * 1.0000004f;
+            const float rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
+            const float rF = fmin_(fmin_(fmax_(rx0, rx1), fmax_(ry0, ry1)), fmax_(rz0, rz1)) * 1.0000004f;
+            const bool hl = lN <= fmin_(lF, closest);
+            const bool hr = rN <= fmin_(rF, closest);
+            const int32_t cl = (int32_t)f2u(n3.x), cr = (int32_t)f2u(n3.y);
+            if (hl && hr) {
+                const bool left_first = lN <= rN;
+                node = left_first ? cl : cr;
+                if (sp < VCRT_FAST_STACK) stack[sp++] = left_first ? cr : cl;
+            } else if (hl) {
+                node = cl;
+            } else if (hr) {
+                node = cr;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            const int32_t slot = ~node;
+            const float4* p = s.ftris + 3 * (size_t)slot;
+            const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
+            if (COUNT) st.tris++;
+            float t;
+            if (tri_test(xyz(a), xyz(b), xyz(c), r, t) && t > VCRT_T_MIN && (t < closest || (t == closest && slot < best))) {
+                closest = t;
+                best = slot;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    if (best < 0) return false;
+    const float4* p = s.ftris + 3 * (size_t)best;
+    const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
+    finish_triangle_hit(xyz(a), xyz(b), xyz(c), f2u(b.w), (int)f2u(a.w), r, closest, rec);
+    return true;
+}
+
+}  // namespace vcrt

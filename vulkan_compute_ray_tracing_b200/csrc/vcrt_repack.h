@@ -1,0 +1,24 @@
+// vcrt_repack.h -- reference bvh[]/triangles[] -> records of the fast traversal (layout: vcrt_fast.cuh).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/vcrt.h"
+
+namespace vcrt {
+
+struct FastBvh {
+    std::vector<float> nodes;      // 16 floats per inner node
+    std::vector<float> tris;       // 12 floats per triangle slot
+    int32_t root = (int32_t)0x80000000;
+    uint32_t depth = 0;            // deepest leaf (root = 0)
+    uint32_t num_nodes() const { return (uint32_t)(nodes.size() / 16); }
+    uint32_t num_slots() const { return (uint32_t)(tris.size() / 12); }
+};
+
+// Walks the tree in the reference's visiting order (right child first, ray-trace-compute.comp:301-306) so that
+// triangle slots are numbered by the reference's tie rank.  Returns false (err set) for trees the fast traversal
+// does not represent: cycles / shared subtrees, leaves that also have children, depth beyond the traversal stack.
+bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle* tris, uint32_t ntris, FastBvh& out, std::string& err);
+
+}  // namespace vcrt
