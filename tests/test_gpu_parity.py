@@ -1,0 +1,212 @@
+"""GPU parity tests (pytest -m gpu, run on the B200 box): the CUDA path, called through the C ABI via the
+ComputeMaterial/ComputeModel mirror, against the CPU oracle on the same inputs and against the committed goldens
+rendered by the reference's own shader (oracle/_ref).
+
+Tolerances, stated once:
+  * integer / index outputs (primary-hit triangle, material, back-face flag, ray counts in portable-trig mode): bit-exact;
+  * primary-hit distance t: bit-exact (same fp32 operation order, -fmad=false);
+  * trig_mode=portable: every output bit-exact (rgba8 frames, f32 accumulation);
+  * trig_mode=libm (CUDA sinf/cosf vs glibc, <= 2 ulp apart): rgba8 frames within 1 LSB on >= 99.9 % of pixel-channels,
+    f32 accumulation PSNR >= 45 dB against the oracle at equal sample count.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CAM, GOLDEN, load_png, small_scene
+from oracleharness import make_params
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return 99.0 if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+def frac_within_1lsb(a, b):
+    return float((np.abs(a.astype(int) - b.astype(int)) <= 1).mean())
+
+
+@pytest.fixture(scope="module")
+def gpu_doge(doge):
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 800, 600)
+    yield g
+    g.close()
+
+
+@pytest.mark.parametrize("name,frames,kw", [
+    ("ref_full_b2_s16_800x600_f1.png", 1, {}),
+    ("ref_full_b2_s16_800x600_f4.png", 4, {}),
+    ("ref_full_b2_s16_800x600_f1_refdispatch.png", 1, dict(full_cover=False)),
+])
+def test_dispatch_matches_reference_frames(gpu_doge, name, frames, kw):
+    """computeCommand (vcrt_dispatch) vs golden rgba8 frames of the reference shader (libm trig -> 1-LSB tolerance)."""
+    gpu_doge.material.clearAccum()
+    got = gpu_doge.frames(CAM, frames, **kw)
+    want = load_png(name)
+    assert frac_within_1lsb(got, want) >= 0.999
+    # pixels whose path never reaches a Lambertian bounce carry no sin/cos: alpha and all misses are exact
+    assert np.array_equal(got[..., 3], want[..., 3])
+
+
+def test_dispatch_simple_shader_matches_reference_frame(doge):
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 800, 600, shader="ray-trace-compute-simple")
+    got = g.frames(CAM, 1)
+    g.close()
+    # the simple shader has no transcendental: bit-exact
+    assert np.array_equal(got, load_png("ref_simple_b4_s16_800x600_f1.png"))
+
+
+@pytest.mark.parametrize("trav", ["reference", "fast"])
+def test_primary_hits_bit_exact(gpu_doge, oracle, doge, trav):
+    a = oracle.render(doge, CAM, 800, 600, make_params(sample_count=1), want_aov=True)
+    b = gpu_doge.render(CAM, traversal=trav, accum="rgba8_ref", sample_count=1, want_aov=True)
+    for f in ("triangle", "material", "backFace"):
+        assert np.array_equal(a["aov"][f], b["aov"][f]), f
+    assert same_bits(a["aov"]["t"], b["aov"]["t"])
+    assert int((a["aov"]["triangle"] >= 0).sum()) == 131420 + 34614 + 6093 + 1762
+
+
+@pytest.mark.parametrize("trav", ["reference", "fast"])
+@pytest.mark.parametrize("shader,nb", [("full", 2), ("full", 8), ("simple", 4)])
+def test_portable_trig_everything_bit_exact(gpu_doge, oracle, doge, trav, shader, nb):
+    w, h = 800, 600
+    for accum, rng, spp in (("rgba8_ref", "pcg_ref", 3), ("f32", "philox", 2)):
+        kw = dict(shader=shader, max_bounces=nb, sample_count=spp, accum=accum, rng=rng, trig="portable")
+        a = oracle.render(doge, CAM, w, h, make_params(traversal="reference", **kw))
+        b = gpu_doge.render(CAM, traversal=trav, **kw)
+        key = "target" if accum == "rgba8_ref" else "accumf"
+        assert same_bits(a[key], b[key]), (accum, rng)
+        assert a["counters"].rays == b["counters"].rays
+
+
+def test_libm_trig_within_tolerance(gpu_doge, oracle, doge):
+    kw = dict(shader="full", max_bounces=8, sample_count=16, accum="f32", rng="philox", trig="libm")
+    a = oracle.render(doge, CAM, 800, 600, make_params(**kw))["accumf"]
+    b = gpu_doge.render(CAM, traversal="fast", **kw)["accumf"]
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert psnr(a[..., :3] / 16.0, b[..., :3] / 16.0) >= 45.0
+    assert float((np.abs(a - b) > 1e-3).mean()) < 5e-3
+
+
+def test_c2_config_1080p(oracle, doge):
+    """BASELINE config 2 shape: bundled scene, 1920x1080, depth 8, light sampling (4 of the 16 spp checked against the oracle)."""
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 1920, 1080)
+    kw = dict(shader="full", max_bounces=8, sample_count=4, accum="f32", rng="pcg_ref", trig="portable")
+    a = oracle.render(doge, CAM, 1920, 1080, make_params(**kw), want_aov=True)
+    b = g.render(CAM, traversal="fast", want_aov=True, **kw)
+    g.close()
+    assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"])
+    mats = b["aov"]["material"]
+    assert [int((mats == m).sum()) for m in (0, 1, 2, 3)] == [425240, 112140, 20164, 5706]
+
+
+def test_glass_metal_deep_tree(oracle):
+    from gpuharness import GpuScene
+    sc = small_scene(n_tris=5000, seed=5)
+    cam = (0.0, 6.0, 1.5)
+    g = GpuScene(sc, 320, 240)
+    kw = dict(shader="full", max_bounces=8, sample_count=2, accum="f32", trig="portable", stack_depth=64)
+    a = oracle.render(sc, cam, 320, 240, make_params(traversal="reference", **kw), want_aov=True)
+    for trav in ("reference", "fast"):
+        b = g.render(cam, traversal=trav, want_aov=True, **kw)
+        assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), trav
+    # MAX_STACK_DEPTH 16 quirk (tree depth > 13): the reference traversal truncates, identically on both sides
+    kw["stack_depth"] = 16
+    a16 = oracle.render(sc, cam, 320, 240, make_params(traversal="reference", **kw))
+    b16 = g.render(cam, traversal="reference", **kw)
+    g.close()
+    assert same_bits(a16["accumf"], b16["accumf"]) and not same_bits(a16["accumf"], a["accumf"])
+
+
+def test_brute_force_spheres(oracle):
+    from gpuharness import GpuScene
+    sc = small_scene(n_tris=30, seed=4)
+    cam = (0.0, 6.0, 1.5)
+    g = GpuScene(sc, 64, 48)
+    kw = dict(shader="full", traversal="brute_force", max_bounces=4, sample_count=2, accum="rgba8_ref", trig="portable")
+    a = oracle.render(sc, cam, 64, 48, make_params(**kw), want_aov=True)
+    b = g.render(cam, want_aov=True, **kw)
+    g.close()
+    assert same_bits(a["target"], b["target"]) and same_bits(a["aov"], b["aov"])
+
+
+def test_edge_cases(oracle):
+    """Empty scene, single triangle, ragged image sizes (not multiples of 32 / 8 / 4)."""
+    from gpuharness import GpuScene
+    import tinybvh
+    cam = (0.0, 6.0, 1.5)
+    for n, (w, h) in ((1, (33, 17)), (2, (70, 45)), (9, (1, 1)), (50, (37, 61))):
+        sc = small_scene(n_tris=n, seed=n)
+        g = GpuScene(sc, w, h)
+        kw = dict(shader="full", max_bounces=4, sample_count=2, accum="f32", trig="portable")
+        a = oracle.render(sc, cam, w, h, make_params(**kw), want_aov=True)
+        for trav in ("reference", "fast"):
+            b = g.render(cam, traversal=trav, want_aov=True, **kw)
+            assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (n, w, h, trav)
+        g.close()
+    sc = small_scene(n_tris=4, seed=1)
+    empty = dict(sc)
+    empty["triangles"] = np.zeros(0, np.uint8); empty["bvh"] = np.zeros(0, np.uint8); empty["lights"] = np.zeros(0, np.uint8)
+    g = GpuScene(empty, 40, 40)
+    for trav in ("reference", "fast"):
+        b = g.render(cam, traversal=trav, accum="f32", sample_count=1)
+        assert np.all(b["accumf"][..., :3] == 0) and np.all(b["accumf"][..., 3] == 1)
+    g.close()
+
+
+def test_sharding_properties(gpu_doge):
+    """Size-independent properties at full size: tile shards partition the frame bit-exactly; sample slices add up."""
+    kw = dict(shader="full", traversal="fast", max_bounces=4, accum="f32", rng="philox", trig="libm")
+    full = gpu_doge.render(CAM, sample_count=8, **kw)["accumf"]
+    parts = [gpu_doge.render(CAM, sample_count=8, tile_rank=r, tile_count=4, **kw)["accumf"] for r in range(4)]
+    assert same_bits(sum(parts), full)
+    cover = sum((p[..., 3] > 0).astype(int) for p in parts)
+    assert cover.min() == 1 and cover.max() == 1
+    a = gpu_doge.render(CAM, sample_begin=0, sample_count=4, **kw)["accumf"]
+    b = gpu_doge.render(CAM, sample_begin=4, sample_count=4, **kw)["accumf"]
+    assert np.allclose(a + b, full, rtol=1e-6, atol=1e-6)
+    # resume: continuing on top of a reloaded accumulation equals the uninterrupted render bit-for-bit
+    gpu_doge.material.clearAccum()
+    gpu_doge.material.writeAccumF32(a)
+    c = gpu_doge.render(CAM, sample_begin=4, sample_count=4, clear=False, **kw)["accumf"]
+    assert same_bits(c, full)
+
+
+def test_resolve_and_gamma(gpu_doge):
+    kw = dict(shader="full", traversal="fast", max_bounces=2, accum="f32", sample_count=4)
+    acc = gpu_doge.render(CAM, **kw)["accumf"]
+    gpu_doge.material.resolve(4, 0.0)
+    img = gpu_doge.target.read()
+    want = np.rint(np.clip(acc / 4.0, 0, 1) * 255.0).astype(np.uint8)
+    assert np.abs(img.astype(int) - want.astype(int)).max() <= 1
+    gpu_doge.material.resolve(4, 2.2)      # post-process-shader.frag:67-68
+    img = gpu_doge.target.read()
+    want = np.rint(np.clip(acc[..., :3] / 4.0, 0, 1) ** (1 / 2.2) * 255.0).astype(np.uint8)
+    assert np.abs(img[..., :3].astype(int) - want.astype(int)).max() <= 1
+
+
+def test_error_behaviour(doge):
+    import ctypes as C
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from vulkan_compute_ray_tracing_b200 import _native
+    L = _native.lib()
+    ctx = C.c_void_p()
+    assert L.vcrt_create(0, C.byref(ctx)) == 0
+    assert L.vcrt_dispatch(ctx, 1, 1, 1) < 0 and b"no storage images" in L.vcrt_last_error(ctx)
+    assert L.vcrt_set_buffer(ctx, 3, doge["triangles"].ctypes.data, 47) < 0
+    assert L.vcrt_set_buffer(ctx, 9, None, 0) < 0
+    assert L.vcrt_set_shader(ctx, b"nope.spv") < 0 and b"failed to" in L.vcrt_last_error(ctx)
+    assert L.vcrt_create(99, C.byref(C.c_void_p())) < 0
+    L.vcrt_destroy(ctx)
+    with pytest.raises(vcrt.VcrtError):
+        vcrt.ComputeMaterial("bogus.spv").bind(None, 0)
