@@ -145,6 +145,10 @@ int vcrt_write_accum_f32(vcrt_ctx* ctx, const void* src, size_t bytes); /* resum
 /* Device pointers of ctx-owned images, for collectives (NCCL) and zero-copy consumers. */
 int vcrt_device_ptr(vcrt_ctx* ctx, int what /* 0 target rgba8, 1 accum rgba8, 2 accum f32, 3 aov */, void** out, size_t* bytes);
 
+/* Run ctx's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores ctx's own stream), so
+ * that renders order with the caller's collectives / events without extra synchronisation.  Synchronises first. */
+int vcrt_set_stream(vcrt_ctx* ctx, void* cuda_stream);
+
 int vcrt_synchronize(vcrt_ctx* ctx);
 int vcrt_get_counters(vcrt_ctx* ctx, vcrt_counters* out);           /* synchronises */
 int vcrt_reset_counters(vcrt_ctx* ctx);

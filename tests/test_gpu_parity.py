@@ -120,12 +120,19 @@ def test_glass_metal_deep_tree(oracle):
     for trav in ("reference", "fast"):
         b = g.render(cam, traversal=trav, want_aov=True, **kw)
         assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), trav
-    # MAX_STACK_DEPTH 16 quirk (tree depth > 13): the reference traversal truncates, identically on both sides
+    g.close()
+    # MAX_STACK_DEPTH 16 quirk (tree depth > 13 <=> more than 8192 triangles): the reference traversal truncates,
+    # identically on both sides
+    sc = small_scene(n_tris=20000, seed=3)
+    g = GpuScene(sc, 96, 64)
+    kw.update(sample_count=1, max_bounces=2)
+    a64 = oracle.render(sc, cam, 96, 64, make_params(traversal="reference", **kw))
     kw["stack_depth"] = 16
-    a16 = oracle.render(sc, cam, 320, 240, make_params(traversal="reference", **kw))
+    a16 = oracle.render(sc, cam, 96, 64, make_params(traversal="reference", **kw))
     b16 = g.render(cam, traversal="reference", **kw)
     g.close()
-    assert same_bits(a16["accumf"], b16["accumf"]) and not same_bits(a16["accumf"], a["accumf"])
+    assert a16["counters"].max_stack == 16
+    assert same_bits(a16["accumf"], b16["accumf"]) and not same_bits(a16["accumf"], a64["accumf"])
 
 
 def test_brute_force_spheres(oracle):

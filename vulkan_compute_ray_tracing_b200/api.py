@@ -228,6 +228,11 @@ class ComputeMaterial:
         self._check(N.lib().vcrt_device_ptr(self._ctx, what, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def setStream(self, cuda_stream):
+        """Run on a caller-owned CUDA stream (integer cudaStream_t handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._require()
+        self._check(N.lib().vcrt_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
     def synchronize(self):
         self._require()
         self._check(N.lib().vcrt_synchronize(self._ctx))

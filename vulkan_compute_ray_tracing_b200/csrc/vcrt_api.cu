@@ -24,6 +24,7 @@ struct DevBuf {
 struct vcrt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     std::string error;
     int shader = VCRT_SHADER_FULL;
     DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
@@ -98,7 +99,16 @@ int vcrt_create(int device, vcrt_ctx** out) {
         delete c;
         return rc;
     }
+    c->own_stream = c->stream;
     *out = c;
+    return VCRT_OK;
+}
+
+int vcrt_set_stream(vcrt_ctx* c, void* cuda_stream) {
+    if (!c) return VCRT_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return VCRT_OK;
 }
 
@@ -110,7 +120,7 @@ int vcrt_destroy(vcrt_ctx* c) {
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
     for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov}) if (b->ptr) cudaFree(b->ptr);
     if (c->d_counters) cudaFree(c->d_counters);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return VCRT_OK;
 }
