@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--traversal", default="fast")
     ap.add_argument("--ref-frames", type=int, default=1, help="1-spp frames per step of the CPU reference arm")
+    ap.add_argument("--static-kernel", action="store_true", help="A/B: one-thread-per-pixel launch of the fast traversal")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -226,7 +227,8 @@ def main():
     mat.setStream(stream.cuda_stream)
 
     params = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
-                                stack_depth=64, sample_begin=rank * args.spp, sample_count=args.spp, philox_seed=args.scene_seed)
+                                stack_depth=64, sample_begin=rank * args.spp, sample_count=args.spp, philox_seed=args.scene_seed,
+                                flags=vcrt.FLAG_STATIC_KERNEL if args.static_kernel else 0)
     ptr, nbytes = mat.devicePtr(2)
 
     class _Wrap:

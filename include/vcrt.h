@@ -64,7 +64,8 @@ enum { VCRT_TRIG_LIBM = 0,      /* platform sinf/cosf (glibc on the CPU, CUDA li
 
 enum { VCRT_FLAG_REF_DISPATCH_COVERAGE = 1u, /* only floor(W/32)*32 x floor(H/32)*32 pixels, as main.cpp:228 dispatches */
        VCRT_FLAG_WRITE_AOV = 2u,             /* primary-hit AOV (vcrt_aov per pixel) */
-       VCRT_FLAG_COUNT_TRAVERSAL = 4u        /* count node/triangle fetches (slower kernel variant) */ };
+       VCRT_FLAG_COUNT_TRAVERSAL = 4u,       /* count node/triangle fetches (slower kernel variant) */
+       VCRT_FLAG_STATIC_KERNEL = 8u          /* fast traversal in the one-thread-per-pixel launch instead of persistent warps (A/B) */ };
 
 typedef struct {
     uint32_t struct_size;    /* = sizeof(vcrt_render_params) */

@@ -36,8 +36,7 @@ class GpuScene:
     def render(self, cam, **kw):
         want_aov = kw.pop("want_aov", False)
         clear = kw.pop("clear", True)
-        if want_aov:
-            kw["flags"] = kw.get("flags", 0) | vcrt.FLAG_WRITE_AOV
+        kw["flags"] = kw.get("flags", 0) | (vcrt.FLAG_WRITE_AOV if want_aov else 0)
         p = vcrt.render_params(**kw)
         self.set_camera(cam, 0)
         if clear:

@@ -65,24 +65,29 @@ def test_dispatch_simple_shader_matches_reference_frame(doge):
     assert np.array_equal(got, load_png("ref_simple_b4_s16_800x600_f1.png"))
 
 
-@pytest.mark.parametrize("trav", ["reference", "fast"])
+def trav_kw(trav):
+    """'fast' = persistent-warps kernel (default), 'fast_static' = the same traversal in the one-thread-per-pixel launch."""
+    return dict(traversal="fast", flags=8) if trav == "fast_static" else dict(traversal=trav)
+
+
+@pytest.mark.parametrize("trav", ["reference", "fast", "fast_static"])
 def test_primary_hits_bit_exact(gpu_doge, oracle, doge, trav):
     a = oracle.render(doge, CAM, 800, 600, make_params(sample_count=1), want_aov=True)
-    b = gpu_doge.render(CAM, traversal=trav, accum="rgba8_ref", sample_count=1, want_aov=True)
+    b = gpu_doge.render(CAM, accum="rgba8_ref", sample_count=1, want_aov=True, **trav_kw(trav))
     for f in ("triangle", "material", "backFace"):
         assert np.array_equal(a["aov"][f], b["aov"][f]), f
     assert same_bits(a["aov"]["t"], b["aov"]["t"])
     assert int((a["aov"]["triangle"] >= 0).sum()) == 131420 + 34614 + 6093 + 1762
 
 
-@pytest.mark.parametrize("trav", ["reference", "fast"])
+@pytest.mark.parametrize("trav", ["reference", "fast", "fast_static"])
 @pytest.mark.parametrize("shader,nb", [("full", 2), ("full", 8), ("simple", 4)])
 def test_portable_trig_everything_bit_exact(gpu_doge, oracle, doge, trav, shader, nb):
     w, h = 800, 600
     for accum, rng, spp in (("rgba8_ref", "pcg_ref", 3), ("f32", "philox", 2)):
         kw = dict(shader=shader, max_bounces=nb, sample_count=spp, accum=accum, rng=rng, trig="portable")
         a = oracle.render(doge, CAM, w, h, make_params(traversal="reference", **kw))
-        b = gpu_doge.render(CAM, traversal=trav, **kw)
+        b = gpu_doge.render(CAM, **trav_kw(trav), **kw)
         key = "target" if accum == "rgba8_ref" else "accumf"
         assert same_bits(a[key], b[key]), (accum, rng)
         assert a["counters"].rays == b["counters"].rays
@@ -117,8 +122,8 @@ def test_glass_metal_deep_tree(oracle):
     g = GpuScene(sc, 320, 240)
     kw = dict(shader="full", max_bounces=8, sample_count=2, accum="f32", trig="portable", stack_depth=64)
     a = oracle.render(sc, cam, 320, 240, make_params(traversal="reference", **kw), want_aov=True)
-    for trav in ("reference", "fast"):
-        b = g.render(cam, traversal=trav, want_aov=True, **kw)
+    for trav in ("reference", "fast", "fast_static"):
+        b = g.render(cam, want_aov=True, **trav_kw(trav), **kw)
         assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), trav
     g.close()
     # MAX_STACK_DEPTH 16 quirk (tree depth > 13 <=> more than 8192 triangles): the reference traversal truncates,
@@ -157,16 +162,16 @@ def test_edge_cases(oracle):
         g = GpuScene(sc, w, h)
         kw = dict(shader="full", max_bounces=4, sample_count=2, accum="f32", trig="portable")
         a = oracle.render(sc, cam, w, h, make_params(**kw), want_aov=True)
-        for trav in ("reference", "fast"):
-            b = g.render(cam, traversal=trav, want_aov=True, **kw)
+        for trav in ("reference", "fast", "fast_static"):
+            b = g.render(cam, want_aov=True, **trav_kw(trav), **kw)
             assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (n, w, h, trav)
         g.close()
     sc = small_scene(n_tris=4, seed=1)
     empty = dict(sc)
     empty["triangles"] = np.zeros(0, np.uint8); empty["bvh"] = np.zeros(0, np.uint8); empty["lights"] = np.zeros(0, np.uint8)
     g = GpuScene(empty, 40, 40)
-    for trav in ("reference", "fast"):
-        b = g.render(cam, traversal=trav, accum="f32", sample_count=1)
+    for trav in ("reference", "fast", "fast_static"):
+        b = g.render(cam, accum="f32", sample_count=1, **trav_kw(trav))
         assert np.all(b["accumf"][..., :3] == 0) and np.all(b["accumf"][..., 3] == 1)
     g.close()
 

@@ -26,72 +26,94 @@ namespace vcrt {
 VCRT_HD float fmin_(float a, float b) { return fminf(a, b); }
 VCRT_HD float fmax_(float a, float b) { return fmaxf(a, b); }
 
+// Per-ray traversal state, advanced one node at a time so that the persistent kernel (vcrt_persistent.cuh) can
+// interleave the rays of a warp; hit_bvh_fast below runs the same steps to completion for one ray.
+struct TravState {
+    float3 idir, ood;       // 1/d (guarded) and o/d for the fma slab test
+    float closest;
+    int32_t best;           // winning triangle slot or -1
+    int32_t node;           // >= 0 inner node to visit, < 0 leaf (~slot), VCRT_FAST_EMPTY: nothing left
+    int sp;
+};
+
+VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
+    const float tiny = 1e-30f;   // guard so that 0 * inf never appears
+    t.idir = f3(1.0f / (fabsf(r.d.x) > tiny ? r.d.x : copysignf(tiny, r.d.x)),
+                1.0f / (fabsf(r.d.y) > tiny ? r.d.y : copysignf(tiny, r.d.y)),
+                1.0f / (fabsf(r.d.z) > tiny ? r.d.z : copysignf(tiny, r.d.z)));
+    t.ood = f3(r.o.x * t.idir.x, r.o.y * t.idir.y, r.o.z * t.idir.z);
+    t.closest = VCRT_T_MAX;
+    t.best = -1;
+    t.node = s.froot;
+    t.sp = 0;
+}
+
+// Visit inner node t.node: test both children, descend into the nearer hit child, push the farther one.
+VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
+    const float4* p = s.fnodes + 4 * (size_t)t.node;
+    const float4 n0 = ldg4(p), n1 = ldg4(p + 1), n2 = ldg4(p + 2), n3 = ldg4(p + 3);
+    const float lx0 = fmaf(n0.x, t.idir.x, -t.ood.x), lx1 = fmaf(n0.y, t.idir.x, -t.ood.x);
+    const float ly0 = fmaf(n0.z, t.idir.y, -t.ood.y), ly1 = fmaf(n0.w, t.idir.y, -t.ood.y);
+    const float lz0 = fmaf(n2.x, t.idir.z, -t.ood.z), lz1 = fmaf(n2.y, t.idir.z, -t.ood.z);
+    const float rx0 = fmaf(n1.x, t.idir.x, -t.ood.x), rx1 = fmaf(n1.y, t.idir.x, -t.ood.x);
+    const float ry0 = fmaf(n1.z, t.idir.y, -t.ood.y), ry1 = fmaf(n1.w, t.idir.y, -t.ood.y);
+    const float rz0 = fmaf(n2.z, t.idir.z, -t.ood.z), rz1 = fmaf(n2.w, t.idir.z, -t.ood.z);
+    const float lN = fmax_(fmax_(fmin_(lx0, lx1), fmin_(ly0, ly1)), fmax_(fmin_(lz0, lz1), 0.0f));
+    const float lF = fmin_(fmin_(fmax_(lx0, lx1), fmax_(ly0, ly1)), fmax_(lz0, lz1)) * 1.0000004f;
+    const float rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
+    const float rF = fmin_(fmin_(fmax_(rx0, rx1), fmax_(ry0, ry1)), fmax_(rz0, rz1)) * 1.0000004f;
+    const bool hl = lN <= fmin_(lF, t.closest);
+    const bool hr = rN <= fmin_(rF, t.closest);
+    const int32_t cl = (int32_t)f2u(n3.x), cr = (int32_t)f2u(n3.y);
+    if (hl && hr) {
+        const bool left_first = lN <= rN;
+        t.node = left_first ? cl : cr;
+        if (t.sp < VCRT_FAST_STACK) stack[t.sp++] = left_first ? cr : cl;
+    } else if (hl) {
+        t.node = cl;
+    } else if (hr) {
+        t.node = cr;
+    } else {
+        t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
+    }
+}
+
+// Test the triangle of leaf code `leaf` (= ~slot) with the reference's arithmetic and tie rule.
+VCRT_HD void trav_leaf_test(TravState& t, const SceneView& s, const Ray& r, int32_t leaf) {
+    const int32_t slot = ~leaf;
+    const float4* p = s.ftris + 3 * (size_t)slot;
+    const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
+    float tt;
+    if (tri_test(xyz(a), xyz(b), xyz(c), r, tt) && tt > VCRT_T_MIN && (tt < t.closest || (tt == t.closest && slot < t.best))) {
+        t.closest = tt;
+        t.best = slot;
+    }
+}
+
+VCRT_HD bool trav_finish(const TravState& t, const SceneView& s, const Ray& r, Hit& rec) {
+    if (t.best < 0) return false;
+    const float4* p = s.ftris + 3 * (size_t)t.best;
+    const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
+    finish_triangle_hit(xyz(a), xyz(b), xyz(c), f2u(b.w), (int)f2u(a.w), r, t.closest, rec);
+    return true;
+}
+
 template <bool COUNT>
 VCRT_HD bool hit_bvh_fast(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
-    int32_t node = s.froot;
-    if (node == VCRT_FAST_EMPTY) return false;
-
-    // 1/d with a guard so that 0 * inf never appears; ood = o/d for the fma slab form
-    const float tiny = 1e-30f;
-    float3 idir = f3(1.0f / (fabsf(r.d.x) > tiny ? r.d.x : copysignf(tiny, r.d.x)),
-                     1.0f / (fabsf(r.d.y) > tiny ? r.d.y : copysignf(tiny, r.d.y)),
-                     1.0f / (fabsf(r.d.z) > tiny ? r.d.z : copysignf(tiny, r.d.z)));
-    float3 ood = f3(r.o.x * idir.x, r.o.y * idir.y, r.o.z * idir.z);
-
-    float closest = VCRT_T_MAX;
-    int32_t best = -1;
+    TravState t;
+    trav_begin(t, s, r);
     int32_t stack[VCRT_FAST_STACK];
-    int sp = 0;
-
-    for (;;) {
-        if (node >= 0) {
-            const float4* p = s.fnodes + 4 * (size_t)node;
-            const float4 n0 = ldg4(p), n1 = ldg4(p + 1), n2 = ldg4(p + 2), n3 = ldg4(p + 3);
+    while (t.node != VCRT_FAST_EMPTY) {
+        if (t.node >= 0) {
             if (COUNT) st.nodes++;
-            const float lx0 = fmaf(n0.x, idir.x, -ood.x), lx1 = fmaf(n0.y, idir.x, -ood.x);
-            const float ly0 = fmaf(n0.z, idir.y, -ood.y), ly1 = fmaf(n0.w, idir.y, -ood.y);
-            const float lz0 = fmaf(n2.x, idir.z, -ood.z), lz1 = fmaf(n2.y, idir.z, -ood.z);
-            const float rx0 = fmaf(n1.x, idir.x, -ood.x), rx1 = fmaf(n1.y, idir.x, -ood.x);
-            const float ry0 = fmaf(n1.z, idir.y, -ood.y), ry1 = fmaf(n1.w, idir.y, -ood.y);
-            const float rz0 = fmaf(n2.z, idir.z, -ood.z), rz1 = fmaf(n2.w, idir.z, -ood.z);
-            const float lN = fmax_(fmax_(fmin_(lx0, lx1), fmin_(ly0, ly1)), fmax_(fmin_(lz0, lz1), 0.0f));
-            const float lF = fmin_(fmin_(fmax_(lx0, lx1), fmax_(ly0, ly1)), fmax_(lz0, lz1)) * 1.0000004f;
-            const float rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
-            const float rF = fmin_(fmin_(fmax_(rx0, rx1), fmax_(ry0, ry1)), fmax_(rz0, rz1)) * 1.0000004f;
-            const bool hl = lN <= fmin_(lF, closest);
-            const bool hr = rN <= fmin_(rF, closest);
-            const int32_t cl = (int32_t)f2u(n3.x), cr = (int32_t)f2u(n3.y);
-            if (hl && hr) {
-                const bool left_first = lN <= rN;
-                node = left_first ? cl : cr;
-                if (sp < VCRT_FAST_STACK) stack[sp++] = left_first ? cr : cl;
-            } else if (hl) {
-                node = cl;
-            } else if (hr) {
-                node = cr;
-            } else {
-                if (sp == 0) break;
-                node = stack[--sp];
-            }
+            trav_inner_step(t, s, stack);
         } else {
-            const int32_t slot = ~node;
-            const float4* p = s.ftris + 3 * (size_t)slot;
-            const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
             if (COUNT) st.tris++;
-            float t;
-            if (tri_test(xyz(a), xyz(b), xyz(c), r, t) && t > VCRT_T_MIN && (t < closest || (t == closest && slot < best))) {
-                closest = t;
-                best = slot;
-            }
-            if (sp == 0) break;
-            node = stack[--sp];
+            trav_leaf_test(t, s, r, t.node);
+            t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
         }
     }
-    if (best < 0) return false;
-    const float4* p = s.ftris + 3 * (size_t)best;
-    const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
-    finish_triangle_hit(xyz(a), xyz(b), xyz(c), f2u(b.w), (int)f2u(a.w), r, closest, rec);
-    return true;
+    return trav_finish(t, s, r, rec);
 }
 
 }  // namespace vcrt

@@ -7,6 +7,13 @@
 #include "vcrt_launch.h"
 
 namespace vcrt {
+__device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStats& st);
+}
+#if VCRT_TU_TRAV == 1
+#include "vcrt_persistent.cuh"
+#endif
+
+namespace vcrt {
 
 __device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStats& st) {
     unsigned rays = __reduce_add_sync(0xffffffffu, st.rays);
@@ -35,6 +42,23 @@ template <int SHADER, int RNG_MODE, int TRIG, bool COUNT>
 static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     const uint32_t items = a.owned_tiles * 1024u;
     if (items == 0u) return cudaSuccess;
+#if VCRT_TU_TRAV == 1
+    if (!(a.flags & VCRT_FLAG_STATIC_KERNEL)) {
+        // persistent warps: one resident wave, grid = SM count x resident blocks per SM
+        static int grid = 0;
+        if (grid == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaError_t e;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+                (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_persistent_kernel<SHADER, RNG_MODE, TRIG, COUNT>, VCRT_PBLOCK, 0)) != cudaSuccess)
+                return e;
+            grid = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        const uint32_t needed = (items + VCRT_PBLOCK - 1) / VCRT_PBLOCK;
+        render_persistent_kernel<SHADER, RNG_MODE, TRIG, COUNT><<<needed < (uint32_t)grid ? needed : (uint32_t)grid, VCRT_PBLOCK, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
+#endif
     const uint32_t blocks = (items + VCRT_BLOCK - 1) / VCRT_BLOCK;
     render_static_kernel<SHADER, VCRT_TU_TRAV, RNG_MODE, TRIG, COUNT><<<blocks, VCRT_BLOCK, 0, stream>>>(a);
     return cudaGetLastError();
@@ -42,7 +66,7 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
 
 template <int SHADER, int RNG_MODE, int TRIG>
 static cudaError_t launch_count(const KernelArgs& a, bool count, cudaStream_t stream) {
-#if VCRT_TU_TRAV == VCRT_TRAVERSAL_FAST
+#if VCRT_TU_TRAV == 1  /* VCRT_TRAVERSAL_FAST (an enum, invisible to the preprocessor) */
     if (count) return launch_one<SHADER, RNG_MODE, TRIG, true>(a, stream);
     return launch_one<SHADER, RNG_MODE, TRIG, false>(a, stream);
 #else

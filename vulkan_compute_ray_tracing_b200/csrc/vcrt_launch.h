@@ -4,6 +4,7 @@
 #include "vcrt_path.cuh"
 
 #define VCRT_BLOCK 128
+#define VCRT_PBLOCK 128   /* persistent kernel */
 
 namespace vcrt {
 cudaError_t launch_render_reference(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
