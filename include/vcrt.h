@@ -146,6 +146,10 @@ int vcrt_write_accum_f32(vcrt_ctx* ctx, const void* src, size_t bytes); /* resum
 /* Device pointers of ctx-owned images, for collectives (NCCL) and zero-copy consumers. */
 int vcrt_device_ptr(vcrt_ctx* ctx, int what /* 0 target rgba8, 1 accum rgba8, 2 accum f32, 3 aov */, void** out, size_t* bytes);
 
+/* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
+ * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology). */
+int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
+
 /* Run ctx's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores ctx's own stream), so
  * that renders order with the caller's collectives / events without extra synchronisation.  Synchronises first. */
 int vcrt_set_stream(vcrt_ctx* ctx, void* cuda_stream);

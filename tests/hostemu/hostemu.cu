@@ -49,6 +49,10 @@ extern "C" int hostemu_render(const void* tris, uint32_t ntris, const void* mats
             if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
             return -1;
         }
+        if (!(p->_reserved & 1u) && !rebuild_fast_bvh_sah(fb, e)) {   // test hook: _reserved bit 0 keeps the bound topology
+            if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
+            return -1;
+        }
         s.fnodes = (const float4*)fb.nodes.data(); s.ftris = (const float4*)fb.tris.data(); s.nfnodes = fb.num_nodes(); s.froot = fb.root;
     }
     const bool ref_cov = (p->flags & VCRT_FLAG_REF_DISPATCH_COVERAGE) != 0;

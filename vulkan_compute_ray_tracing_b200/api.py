@@ -228,6 +228,11 @@ class ComputeMaterial:
         self._check(N.lib().vcrt_device_ptr(self._ctx, what, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def setOption(self, key, value):
+        """Tunables that do not change results, e.g. ("fast_bvh", "sah" | "topology")."""
+        self._require()
+        self._check(N.lib().vcrt_set_option(self._ctx, key.encode(), value.encode()))
+
     def setStream(self, cuda_stream):
         """Run on a caller-owned CUDA stream (integer cudaStream_t handle, e.g. torch.cuda.current_stream().cuda_stream)."""
         self._require()

@@ -30,6 +30,7 @@ struct vcrt_ctx {
     DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
     std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
     bool fast_dirty = true;
+    bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
     bool fast_ok = false;
     std::string fast_err;
     DevBuf fnodes, ftris;
@@ -102,6 +103,18 @@ int vcrt_create(int device, vcrt_ctx** out) {
     c->own_stream = c->stream;
     *out = c;
     return VCRT_OK;
+}
+
+int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
+    if (!c || !key || !value) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: NULL argument");
+    const std::string k(key), v(value);
+    if (k == "fast_bvh") {
+        if (v != "sah" && v != "topology") return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: fast_bvh must be 'sah' or 'topology'");
+        const bool sah = v == "sah";
+        if (sah != c->fast_sah) { c->fast_sah = sah; c->fast_dirty = true; }
+        return VCRT_OK;
+    }
+    return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: unknown option '" + k + "'");
 }
 
 int vcrt_set_stream(vcrt_ctx* c, void* cuda_stream) {
@@ -200,6 +213,7 @@ static int prepare_fast(vcrt_ctx* c) {
         c->fast_err.clear();
         c->fast_ok = build_fast_bvh((const vcrt_bvh_node*)c->host_bvh.data(), (uint32_t)(c->host_bvh.size() / sizeof(vcrt_bvh_node)),
                                     (const vcrt_triangle*)c->host_tris.data(), (uint32_t)(c->host_tris.size() / sizeof(vcrt_triangle)), fb, c->fast_err);
+        if (c->fast_ok && c->fast_sah) c->fast_ok = rebuild_fast_bvh_sah(fb, c->fast_err);
         c->fast_dirty = false;
         if (c->fast_ok) {
             int rc;

@@ -1,5 +1,7 @@
 #include "vcrt_repack.h"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -72,6 +74,137 @@ bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle
         }
     }
     if (out.depth + 2 > 48) { err = "bvh: depth " + std::to_string(out.depth) + " exceeds the fast traversal stack (46)"; return false; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ SAH rebuild
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { lo[0] = lo[1] = lo[2] = std::numeric_limits<float>::infinity(); hi[0] = hi[1] = hi[2] = -std::numeric_limits<float>::infinity(); }
+    void grow(const Box& b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float half_area() const { const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return dx * dy + dy * dz + dz * dx; }
+};
+
+struct Prim { Box box; float c[3]; int32_t slot; };
+
+struct SahBuilder {
+    std::vector<Prim> prims;
+    std::vector<float> nodes;     // 16 floats per inner node, preallocated (n - 1)
+    std::atomic<uint32_t> max_depth{0};
+
+    // Builds the subtree over prims[b,e) (e - b >= 2) into node index b (nodes b .. e-2 belong to this subtree: a binary
+    // tree over m leaves has m-1 inner nodes, so the left subtree [b,mid) takes b+1 .. and the right one mid .. ; the
+    // layout is therefore independent of the task schedule).  Returns the subtree bounds through `out`.
+    void build(uint32_t b, uint32_t e, uint32_t node, uint32_t depth, Box& out) {
+        const uint32_t n = e - b;
+        Box bounds, cb;
+        bounds.reset(); cb.reset();
+        for (uint32_t i = b; i < e; ++i) { bounds.grow(prims[i].box); cb.grow(prims[i].c); }
+        out = bounds;
+        uint32_t mid = b + n / 2;
+        bool split_found = false;
+        if (n > 2 && depth < 24) {   // past depth 24 only median splits: depth <= 24 + log2(n) stays inside the traversal stack
+            constexpr int NB = 16;
+            float best_cost = std::numeric_limits<float>::infinity();
+            int best_axis = -1, best_bin = -1;
+            for (int a = 0; a < 3; ++a) {
+                const float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.0f)) continue;
+                const float k = NB * (1.0f - 1e-6f) / ext;
+                Box bb[NB]; uint32_t cnt[NB];
+                for (int i = 0; i < NB; ++i) { bb[i].reset(); cnt[i] = 0; }
+                for (uint32_t i = b; i < e; ++i) {
+                    int bin = (int)((prims[i].c[a] - cb.lo[a]) * k);
+                    bin = bin < 0 ? 0 : (bin >= NB ? NB - 1 : bin);
+                    bb[bin].grow(prims[i].box); cnt[bin]++;
+                }
+                float right_area[NB]; uint32_t right_cnt[NB];
+                Box acc; acc.reset(); uint32_t c = 0;
+                for (int i = NB - 1; i > 0; --i) { acc.grow(bb[i]); c += cnt[i]; right_area[i] = acc.half_area(); right_cnt[i] = c; }
+                acc.reset(); c = 0;
+                for (int i = 0; i < NB - 1; ++i) {
+                    acc.grow(bb[i]); c += cnt[i];
+                    if (c == 0 || right_cnt[i + 1] == 0) continue;
+                    const float cost = acc.half_area() * (float)c + right_area[i + 1] * (float)right_cnt[i + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = i; }
+                }
+            }
+            if (best_axis >= 0) {
+                const int a = best_axis;
+                const float k = NB * (1.0f - 1e-6f) / (cb.hi[a] - cb.lo[a]);
+                auto it = std::partition(prims.begin() + b, prims.begin() + e, [&](const Prim& p) {
+                    int bin = (int)((p.c[a] - cb.lo[a]) * k);
+                    bin = bin < 0 ? 0 : (bin >= NB ? NB - 1 : bin);
+                    return bin <= best_bin;
+                });
+                mid = (uint32_t)(it - prims.begin());
+                split_found = mid > b && mid < e;
+            }
+        }
+        if (!split_found) {   // degenerate centroids, tiny ranges or the depth cap: median on the widest centroid axis
+            mid = b + n / 2;
+            int a = 0;
+            if (cb.hi[1] - cb.lo[1] > cb.hi[a] - cb.lo[a]) a = 1;
+            if (cb.hi[2] - cb.lo[2] > cb.hi[a] - cb.lo[a]) a = 2;
+            std::nth_element(prims.begin() + b, prims.begin() + mid, prims.begin() + e, [a](const Prim& x, const Prim& y) { return x.c[a] < y.c[a]; });
+        }
+        Box lb, rb;
+        int32_t lcode, rcode;
+        const uint32_t nl = mid - b, nr = e - mid;
+        // node numbering: this node = `node`; left subtree's inner nodes follow immediately, then the right subtree's
+        const uint32_t lnode = node + 1, rnode = node + 1 + (nl - 1);
+        auto child = [&](uint32_t cb_, uint32_t ce_, uint32_t cnode, Box& bx, int32_t& code) {
+            if (ce_ - cb_ == 1) { bx = prims[cb_].box; code = ~prims[cb_].slot; uint32_t d = depth + 1, m = max_depth.load(); while (d > m && !max_depth.compare_exchange_weak(m, d)) {} }
+            else { build(cb_, ce_, cnode, depth + 1, bx); code = (int32_t)cnode; }
+        };
+        if (n > 8192) {
+#pragma omp task shared(lb, lcode) firstprivate(b, mid, lnode)
+            child(b, mid, lnode, lb, lcode);
+#pragma omp task shared(rb, rcode) firstprivate(mid, e, rnode)
+            child(mid, e, rnode, rb, rcode);
+#pragma omp taskwait
+        } else {
+            child(b, mid, lnode, lb, lcode);
+            child(mid, e, rnode, rb, rcode);
+        }
+        (void)nr;
+        float* p = &nodes[(size_t)node * 16];
+        p[0] = lb.lo[0]; p[1] = lb.hi[0]; p[2] = lb.lo[1]; p[3] = lb.hi[1]; p[8] = lb.lo[2]; p[9] = lb.hi[2];
+        p[4] = rb.lo[0]; p[5] = rb.hi[0]; p[6] = rb.lo[1]; p[7] = rb.hi[1]; p[10] = rb.lo[2]; p[11] = rb.hi[2];
+        p[12] = bits(lcode); p[13] = bits(rcode); p[14] = p[15] = 0.0f;
+    }
+};
+
+}  // namespace
+
+bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err) {
+    const uint32_t n = fb.num_slots();
+    if (n < 2) return true;   // empty scene or a single leaf: nothing to restructure
+    SahBuilder sb;
+    sb.prims.resize(n);
+    const float eps = 0.0001f;   // the reference's leaf padding (Bvh.h:16)
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* t = &fb.tris[(size_t)i * 12];
+        Prim& p = sb.prims[i];
+        for (int a = 0; a < 3; ++a) {
+            const float lo = std::min(std::min(t[a], t[4 + a]), t[8 + a]), hi = std::max(std::max(t[a], t[4 + a]), t[8 + a]);
+            p.box.lo[a] = lo - eps; p.box.hi[a] = hi + eps;
+            p.c[a] = 0.5f * (lo + hi);
+        }
+        p.slot = (int32_t)i;
+    }
+    sb.nodes.assign((size_t)(n - 1) * 16, 0.0f);
+    Box root;
+#pragma omp parallel
+#pragma omp single
+    sb.build(0, n, 0, 0, root);
+    if (sb.max_depth.load() + 2 > 48) { err = "sah rebuild: depth " + std::to_string(sb.max_depth.load()) + " exceeds the fast traversal stack"; return false; }
+    fb.nodes.swap(sb.nodes);
+    fb.root = 0;
+    fb.depth = sb.max_depth.load();
     return true;
 }
 

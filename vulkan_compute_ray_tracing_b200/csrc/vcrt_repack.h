@@ -21,4 +21,10 @@ struct FastBvh {
 // does not represent: cycles / shared subtrees, leaves that also have children, depth beyond the traversal stack.
 bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle* tris, uint32_t ntris, FastBvh& out, std::string& err);
 
+// Same records, but over a topology built here: binned-SAH top-down build over the leaves collected above (their
+// triangles keep their slots = the reference's tie ranks, so results do not change; only the number of nodes a ray
+// visits does).  The reference's builder splits at the median of a random axis (Bvh.h:160,175), which costs several
+// times more node visits per ray than a surface-area-heuristic tree.  Parallel over subtrees (OpenMP tasks).
+bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err);
+
 }  // namespace vcrt
