@@ -56,7 +56,7 @@ enum { VCRT_TRAVERSAL_REFERENCE = 0, /* hit_bvh exactly as written (ray-trace-co
        VCRT_TRAVERSAL_FAST = 1,      /* same closest hit (same tie rule), repacked nodes, ordered + t-culled, persistent warps */
        VCRT_TRAVERSAL_BRUTE_FORCE = 2/* hit_scene (:222-247): all triangles, then all spheres; the only mode that sees spheres */ };
 enum { VCRT_RNG_PCG_REF = 0,    /* random.glsl:4-22, seed (600*x+y)*(sample+1) */
-       VCRT_RNG_PHILOX = 1      /* Philox4x32-10, key (pixel, seed), counter (sample, draw/4) */ };
+       VCRT_RNG_PHILOX = 1      /* Philox4x32-10, key (pixel, seed), counter (sample, bounce, block-in-bounce, 0) */ };
 enum { VCRT_ACCUM_RGBA8_REF = 0,/* running mean through the rgba8 target/accumulation pair (ray-trace-compute.comp:375-379 + main.cpp:253-261) */
        VCRT_ACCUM_F32 = 1       /* sum of unclamped samples into an RGBA f32 buffer (A counts samples) */ };
 enum { VCRT_TRIG_LIBM = 0,      /* platform sinf/cosf (glibc on the CPU, CUDA libdevice on the GPU): ulp-level differences */
@@ -65,7 +65,8 @@ enum { VCRT_TRIG_LIBM = 0,      /* platform sinf/cosf (glibc on the CPU, CUDA li
 enum { VCRT_FLAG_REF_DISPATCH_COVERAGE = 1u, /* only floor(W/32)*32 x floor(H/32)*32 pixels, as main.cpp:228 dispatches */
        VCRT_FLAG_WRITE_AOV = 2u,             /* primary-hit AOV (vcrt_aov per pixel) */
        VCRT_FLAG_COUNT_TRAVERSAL = 4u,       /* count node/triangle fetches (slower kernel variant) */
-       VCRT_FLAG_STATIC_KERNEL = 8u          /* fast traversal in the one-thread-per-pixel launch instead of persistent warps (A/B) */ };
+       VCRT_FLAG_STATIC_KERNEL = 8u,         /* fast traversal in the one-thread-per-pixel launch (A/B, debugging) */
+       VCRT_FLAG_MEGAKERNEL = 16u            /* fast traversal in the persistent-warps megakernel instead of the wavefront pipeline (A/B) */ };
 
 typedef struct {
     uint32_t struct_size;    /* = sizeof(vcrt_render_params) */

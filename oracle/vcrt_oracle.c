@@ -80,7 +80,7 @@ void vcrt_oracle_sincos_portable(float x, float* s, float* c) {
 typedef struct {
     uint32_t mode;
     uint32_t pcg;                 /* random.glsl:19 state */
-    uint32_t key[2], ctr[2], buf[4], have; /* Philox: key (pixel, seed), counter (sample, block) */
+    uint32_t key[2], ctr[3], buf[4], have; /* Philox: key (pixel, seed), counter (sample, bounce, block-in-bounce) */
 } rng_t;
 
 uint32_t vcrt_oracle_pcg_next(uint32_t* state) { /* random.glsl:4-17, returns `word` */
@@ -107,9 +107,9 @@ static inline float rng_next(rng_t* g) {
         return (float)w / 4294967295.0f; /* float(2^32-1) == 2^32: [0,1] inclusive, random.glsl:16 */
     }
     if (g->have == 0) {
-        uint32_t c[4] = {g->ctr[0], g->ctr[1], 0u, 0u};
+        uint32_t c[4] = {g->ctr[0], g->ctr[1], g->ctr[2], 0u};
         vcrt_oracle_philox4x32_10(c, g->key, g->buf);
-        g->ctr[1]++;
+        g->ctr[2]++;
         g->have = 4;
     }
     uint32_t w = g->buf[4 - g->have];
@@ -341,6 +341,7 @@ static v3 ray_color(const env_t* e, ray_t r, rng_t* g, tally_t* tl, vcrt_aov* ao
     v3 final_color = V3(1.0f, 1.0f, 1.0f);
     ray_t cur = {r.origin, normalize(r.dir)};
     for (uint32_t i = 0; i < e->max_bounces; ++i) {
+        g->ctr[1] = i; g->ctr[2] = 0; g->have = 0; /* Philox: a fresh counter block per bounce (stateless across rays) */
         int hit = closest_hit(e, &cur, &rec, tl);
         if (i == 0 && aov) {
             if (hit) { aov->triangle = rec.triangle; aov->material = (int32_t)rec.materialIndex; aov->t = rec.t; aov->backFace = (uint32_t)rec.backFaceInt; }

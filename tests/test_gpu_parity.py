@@ -66,11 +66,15 @@ def test_dispatch_simple_shader_matches_reference_frame(doge):
 
 
 def trav_kw(trav):
-    """'fast' = persistent-warps kernel (default), 'fast_static' = the same traversal in the one-thread-per-pixel launch."""
-    return dict(traversal="fast", flags=8) if trav == "fast_static" else dict(traversal=trav)
+    """'fast' = wavefront pipeline (default); 'fast_mega' = persistent-warps megakernel; 'fast_static' = one thread per pixel."""
+    if trav == "fast_static":
+        return dict(traversal="fast", flags=8)
+    if trav == "fast_mega":
+        return dict(traversal="fast", flags=16)
+    return dict(traversal=trav)
 
 
-@pytest.mark.parametrize("trav", ["reference", "fast", "fast_static"])
+@pytest.mark.parametrize("trav", ["reference", "fast", "fast_mega", "fast_static"])
 def test_primary_hits_bit_exact(gpu_doge, oracle, doge, trav):
     a = oracle.render(doge, CAM, 800, 600, make_params(sample_count=1), want_aov=True)
     b = gpu_doge.render(CAM, accum="rgba8_ref", sample_count=1, want_aov=True, **trav_kw(trav))
@@ -80,7 +84,7 @@ def test_primary_hits_bit_exact(gpu_doge, oracle, doge, trav):
     assert int((a["aov"]["triangle"] >= 0).sum()) == 131420 + 34614 + 6093 + 1762
 
 
-@pytest.mark.parametrize("trav", ["reference", "fast", "fast_static"])
+@pytest.mark.parametrize("trav", ["reference", "fast", "fast_mega", "fast_static"])
 @pytest.mark.parametrize("shader,nb", [("full", 2), ("full", 8), ("simple", 4)])
 def test_portable_trig_everything_bit_exact(gpu_doge, oracle, doge, trav, shader, nb):
     w, h = 800, 600
@@ -122,7 +126,7 @@ def test_glass_metal_deep_tree(oracle):
     g = GpuScene(sc, 320, 240)
     kw = dict(shader="full", max_bounces=8, sample_count=2, accum="f32", trig="portable", stack_depth=64)
     a = oracle.render(sc, cam, 320, 240, make_params(traversal="reference", **kw), want_aov=True)
-    for trav in ("reference", "fast", "fast_static"):
+    for trav in ("reference", "fast", "fast_mega", "fast_static"):
         b = g.render(cam, want_aov=True, **trav_kw(trav), **kw)
         assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), trav
     g.close()
@@ -162,7 +166,7 @@ def test_edge_cases(oracle):
         g = GpuScene(sc, w, h)
         kw = dict(shader="full", max_bounces=4, sample_count=2, accum="f32", trig="portable")
         a = oracle.render(sc, cam, w, h, make_params(**kw), want_aov=True)
-        for trav in ("reference", "fast", "fast_static"):
+        for trav in ("reference", "fast", "fast_mega", "fast_static"):
             b = g.render(cam, want_aov=True, **trav_kw(trav), **kw)
             assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (n, w, h, trav)
         g.close()
@@ -170,7 +174,7 @@ def test_edge_cases(oracle):
     empty = dict(sc)
     empty["triangles"] = np.zeros(0, np.uint8); empty["bvh"] = np.zeros(0, np.uint8); empty["lights"] = np.zeros(0, np.uint8)
     g = GpuScene(empty, 40, 40)
-    for trav in ("reference", "fast", "fast_static"):
+    for trav in ("reference", "fast", "fast_mega", "fast_static"):
         b = g.render(cam, accum="f32", sample_count=1, **trav_kw(trav))
         assert np.all(b["accumf"][..., :3] == 0) and np.all(b["accumf"][..., 3] == 1)
     g.close()

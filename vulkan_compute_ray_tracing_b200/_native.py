@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvcrt.so")
+LIB_PATH = os.environ.get("VCRT_LIB") or os.path.join(_HERE, "lib", "libvcrt.so")   # VCRT_LIB: development A/B builds only
 
 
 class VcrtError(RuntimeError):

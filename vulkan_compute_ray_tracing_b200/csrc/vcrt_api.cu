@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,10 +31,13 @@ struct vcrt_ctx {
     DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
     std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
     bool fast_dirty = true;
+    uint32_t leaf_threshold = 3, shade_threshold = 10;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
     bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
     bool fast_ok = false;
     std::string fast_err;
     DevBuf fnodes, ftris;
+    DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues
+    uint32_t wf_capacity = 0;
     int32_t froot = (int32_t)0x80000000;
     uint32_t nfnodes = 0;
     uint32_t W = 0, H = 0;
@@ -114,6 +118,12 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         if (sah != c->fast_sah) { c->fast_sah = sah; c->fast_dirty = true; }
         return VCRT_OK;
     }
+    if (k == "leaf_threshold" || k == "shade_threshold") {
+        const int n = atoi(value);
+        if (n < 1 || n > 32) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: threshold must be 1..32 lanes");
+        (k == "leaf_threshold" ? c->leaf_threshold : c->shade_threshold) = (uint32_t)n;
+        return VCRT_OK;
+    }
     return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: unknown option '" + k + "'");
 }
 
@@ -131,7 +141,7 @@ int vcrt_destroy(vcrt_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
-    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov}) if (b->ptr) cudaFree(b->ptr);
+    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts}) if (b->ptr) cudaFree(b->ptr);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -258,6 +268,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     a.target = (uchar4*)c->target.ptr; a.accum8 = (uchar4*)c->accum8.ptr; a.accumf = (float4*)c->accumf.ptr; a.aov = (vcrt_aov*)c->aov.ptr;
     a.counters = c->d_counters;
     a.work_counter = (unsigned int*)(c->d_counters + 3);
+    a.leaf_threshold = c->leaf_threshold; a.shade_threshold = c->shade_threshold;
 
     cudaEvent_t e0, e1;
     CU(c, cudaEventCreate(&e0), "create event");
@@ -266,13 +277,27 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     CU(c, cudaEventRecord(e0, c->stream), "record event");
     const bool count = (p.flags & VCRT_FLAG_COUNT_TRAVERSAL) != 0;
     cudaError_t e;
-    if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
+    uint32_t nlaunch = 1;
+    if (p.traversal == VCRT_TRAVERSAL_FAST && !(p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL))) {
+        // wavefront pipeline: queues sized for a batch of paths (a range of pixels x all samples of the call)
+        const uint32_t want = a.sample_count > (8u << 20) ? a.sample_count : (8u << 20);
+        if (c->wf_capacity < want) {
+            int rc;
+            if ((rc = ensure(c, c->wf_q0, (size_t)want * 48, "allocate ray queue")) || (rc = ensure(c, c->wf_q1, (size_t)want * 48, "allocate ray queue")) ||
+                (rc = ensure(c, c->wf_hit, (size_t)want * 8, "allocate hit buffer")) || (rc = ensure(c, c->wf_color, (size_t)want * 16, "allocate sample buffer")) ||
+                (rc = ensure(c, c->wf_counts, 16, "allocate queue counters"))) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+            c->wf_capacity = want;
+        }
+        nlaunch = 0;
+        e = launch_render_wavefront(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream, (float4*)c->wf_q0.ptr, (float4*)c->wf_q1.ptr,
+                                    (uint2*)c->wf_hit.ptr, (float4*)c->wf_color.ptr, (unsigned int*)c->wf_counts.ptr, c->wf_capacity, &nlaunch);
+    } else if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     else if (p.traversal == VCRT_TRAVERSAL_BRUTE_FORCE) e = launch_render_brute(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     else e = launch_render_reference(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, e, "launch render kernel"); }
     CU(c, cudaEventRecord(e1, c->stream), "record event");
     c->events.emplace_back(e0, e1);
-    c->launches += 1;
+    c->launches += nlaunch;
     return VCRT_OK;
 }
 

@@ -84,9 +84,11 @@ VCRT_HD void sincos_portable(float x, float* s, float* c) {
 
 // ------------------------------------------------------------------------------------------ RNG
 // PCG-RXS-M-XS-32 exactly as include/random.glsl:4-22; Philox4x32-10 for the production mode.
+// Philox stream: key = (pixel, seed), counter = (sample, bounce, block-in-bounce, 0): every bounce starts a fresh
+// block, so no generator state has to survive a traversal and a bounce costs one block (two with light sampling).
 struct Rng {
     uint32_t pcg;
-    uint32_t key0, key1, ctr0, ctr1;
+    uint32_t key0, key1, ctr0, ctr1, ctr2;
     uint32_t buf[4];
     uint32_t have;
 };
@@ -113,8 +115,13 @@ VCRT_HD void rng_init(Rng& g, uint32_t x, uint32_t y, uint32_t pix, uint32_t sam
     if (RNG_MODE == VCRT_RNG_PCG_REF) {
         g.pcg = (600u * x + y) * (sample + 1u);  // random.glsl:19
     } else {
-        g.key0 = pix; g.key1 = seed; g.ctr0 = sample; g.ctr1 = 0u; g.have = 0u;
+        g.key0 = pix; g.key1 = seed; g.ctr0 = sample; g.ctr1 = 0u; g.ctr2 = 0u; g.have = 0u;
     }
+}
+
+template <int RNG_MODE>
+VCRT_HD void rng_begin_bounce(Rng& g, uint32_t bounce) {
+    if (RNG_MODE == VCRT_RNG_PHILOX) { g.ctr1 = bounce; g.ctr2 = 0u; g.have = 0u; }
 }
 
 template <int RNG_MODE>
@@ -132,8 +139,8 @@ VCRT_HD float rng_next(Rng& g) {
 #endif
     } else {
         if (g.have == 0u) {
-            philox4x32_10(g.ctr0, g.ctr1, 0u, 0u, g.key0, g.key1, g.buf);
-            g.ctr1++;
+            philox4x32_10(g.ctr0, g.ctr1, g.ctr2, 0u, g.key0, g.key1, g.buf);
+            g.ctr2++;
             g.have = 4u;
         }
         uint32_t w = g.have == 4u ? g.buf[0] : g.have == 3u ? g.buf[1] : g.have == 2u ? g.buf[2] : g.buf[3];

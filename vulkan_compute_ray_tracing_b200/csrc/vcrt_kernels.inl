@@ -11,6 +11,7 @@ __device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStat
 }
 #if VCRT_TU_TRAV == 1
 #include "vcrt_persistent.cuh"
+#include "vcrt_wavefront.cuh"
 #endif
 
 namespace vcrt {
@@ -43,7 +44,7 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
     const uint32_t items = a.owned_tiles * 1024u;
     if (items == 0u) return cudaSuccess;
 #if VCRT_TU_TRAV == 1
-    if (!(a.flags & VCRT_FLAG_STATIC_KERNEL)) {
+    if (!(a.flags & VCRT_FLAG_STATIC_KERNEL)) {   // VCRT_FLAG_MEGAKERNEL
         // persistent warps: one resident wave, grid = SM count x resident blocks per SM
         static int grid = 0;
         if (grid == 0) {
@@ -91,5 +92,75 @@ cudaError_t VCRT_TU_NAME(const KernelArgs& a, int shader, int rng, int trig, boo
     if (shader == VCRT_SHADER_SIMPLE) return launch_rng<VCRT_SHADER_SIMPLE>(a, rng, trig, count, stream);
     return launch_rng<VCRT_SHADER_FULL>(a, rng, trig, count, stream);
 }
+
+#if VCRT_TU_TRAV == 1
+// ---------------------------------------------------------------------------------------------- wavefront pipeline
+__global__ void wf_reset_kernel(unsigned int* counts, int which) {
+    counts[which] = 0u;   // the queue about to be filled
+    counts[2] = 0u;       // the trace fetch counter
+}
+
+template <int SHADER, int RNG_MODE, int TRIG>
+static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
+    static int trace_grid[2] = {0, 0}, sms = 0;
+    if (sms == 0) {
+        int dev = 0, per_sm = 0;
+        cudaError_t e;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<false>, VCRT_PBLOCK, 0)) != cudaSuccess) return e;
+        trace_grid[0] = sms * (per_sm > 0 ? per_sm : 1);
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<true>, VCRT_PBLOCK, 0)) != cudaSuccess) return e;
+        trace_grid[1] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const uint32_t items = a.owned_tiles * 1024u;
+    const uint32_t per_batch = w.capacity / a.sample_count;   // capacity >= sample_count is guaranteed by the caller
+    const uint32_t shade_grid = (uint32_t)sms * 8u;
+    for (uint32_t item0 = 0; item0 < items; item0 += per_batch) {
+        WfBatch b;
+        b.item0 = item0;
+        b.nitems = items - item0 < per_batch ? items - item0 : per_batch;
+        b.npaths = b.nitems * a.sample_count;
+        b.cur = 0u; b.bounce = 0u;
+        cudaError_t e = cudaMemsetAsync(w.counts, 0, 3 * sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        wf_generate_kernel<RNG_MODE><<<(b.npaths + 255u) / 256u, 256, 0, stream>>>(a, w, b);
+        ++*launches;
+        for (uint32_t bounce = 0; bounce < a.env.max_bounces; ++bounce) {
+            b.bounce = bounce;
+            wf_reset_kernel<<<1, 1, 0, stream>>>(w.counts, (int)(b.cur ^ 1u));
+            if (count) wf_trace_kernel<true><<<trace_grid[1], VCRT_PBLOCK, 0, stream>>>(a, w, b);
+            else wf_trace_kernel<false><<<trace_grid[0], VCRT_PBLOCK, 0, stream>>>(a, w, b);
+            wf_shade_kernel<SHADER, RNG_MODE, TRIG><<<shade_grid, 256, 0, stream>>>(a, w, b);
+            *launches += 3;
+            b.cur ^= 1u;
+        }
+        wf_accumulate_kernel<<<(b.nitems + 255u) / 256u, 256, 0, stream>>>(a, w, b);
+        ++*launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+template <int SHADER, int RNG_MODE>
+static cudaError_t wf_trig(const KernelArgs& a, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
+    if (trig == VCRT_TRIG_PORTABLE) return wf_run<SHADER, RNG_MODE, VCRT_TRIG_PORTABLE>(a, count, stream, w, launches);
+    return wf_run<SHADER, RNG_MODE, VCRT_TRIG_LIBM>(a, count, stream, w, launches);
+}
+
+template <int SHADER>
+static cudaError_t wf_rng(const KernelArgs& a, int rng, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
+    if (rng == VCRT_RNG_PHILOX) return wf_trig<SHADER, VCRT_RNG_PHILOX>(a, trig, count, stream, w, launches);
+    return wf_trig<SHADER, VCRT_RNG_PCG_REF>(a, trig, count, stream, w, launches);
+}
+
+cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream,
+                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches) {
+    if (a.owned_tiles == 0u) return cudaSuccess;
+    WfQueues w;
+    w.q[0] = q0; w.q[1] = q1; w.hit = hit; w.sample_color = sample_color; w.counts = counts; w.capacity = capacity;
+    if (shader == VCRT_SHADER_SIMPLE) return wf_rng<VCRT_SHADER_SIMPLE>(a, rng, trig, count, stream, w, launches);
+    return wf_rng<VCRT_SHADER_FULL>(a, rng, trig, count, stream, w, launches);
+}
+#endif
 
 }  // namespace vcrt

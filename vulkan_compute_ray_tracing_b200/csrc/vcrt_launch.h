@@ -4,9 +4,18 @@
 #include "vcrt_path.cuh"
 
 #define VCRT_BLOCK 128
-#define VCRT_PBLOCK 128   /* persistent kernel */
+#ifndef VCRT_PBLOCK
+#define VCRT_PBLOCK 128   /* persistent kernel: threads per block */
+#endif
+#ifndef VCRT_PMINB
+#define VCRT_PMINB 1     /* persistent kernel: min resident blocks per SM (register cap) */
+#endif
 
 namespace vcrt {
+struct WfQueues;
+// Wavefront pipeline of the fast traversal (vcrt_wavefront.cuh); queues are owned by the context.
+cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream,
+                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches);
 cudaError_t launch_render_reference(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_fast(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_brute(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);

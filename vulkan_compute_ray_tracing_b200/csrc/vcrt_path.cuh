@@ -23,6 +23,7 @@ struct KernelArgs {
     vcrt_aov* aov;
     unsigned long long* counters;        // [0] rays [1] nodes [2] triangles
     unsigned int* work_counter;          // persistent kernels: next work item
+    uint32_t leaf_threshold, shade_threshold;   // persistent kernel phase thresholds (lanes)
 };
 
 // Work item -> pixel.  Items enumerate the owned 32x32 tiles; inside a tile, 32 consecutive items form an
@@ -55,6 +56,7 @@ VCRT_HD float3 ray_color(const KernelArgs& a, const Ray& primary, Rng& g, TraceS
     cur.o = primary.o;
     cur.d = normalize(primary.d);
     for (uint32_t i = 0; i < a.env.max_bounces; ++i) {
+        rng_begin_bounce<RNG_MODE>(g, i);
         bool hit = closest_hit<TRAV, COUNT>(a, cur, rec, st);
         if (i == 0 && aov) {
             if (hit) { aov->triangle = rec.triangle; aov->material = (int32_t)rec.materialIndex; aov->t = rec.t; aov->backFace = (uint32_t)rec.backFaceInt; }

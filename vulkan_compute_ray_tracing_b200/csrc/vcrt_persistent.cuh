@@ -19,35 +19,9 @@
 
 namespace vcrt {
 
-#ifndef VCRT_LEAF_T
-#define VCRT_LEAF_T 10
-#endif
-#ifndef VCRT_SHADE_T
-#define VCRT_SHADE_T 8
-#endif
-
-template <int RNG_MODE>
-__device__ __forceinline__ uint32_t rng_save(const Rng& g) {
-    if (RNG_MODE == VCRT_RNG_PCG_REF) return g.pcg;
-    return g.ctr1 * 4u - g.have;   // draws consumed so far
-}
-
-template <int RNG_MODE>
-__device__ __forceinline__ void rng_restore(Rng& g, uint32_t saved, uint32_t pix, uint32_t sample, uint32_t seed) {
-    if (RNG_MODE == VCRT_RNG_PCG_REF) { g.pcg = saved; return; }
-    g.key0 = pix; g.key1 = seed; g.ctr0 = sample;
-    g.ctr1 = saved >> 2;
-    g.have = 0u;
-    const uint32_t skip = saved & 3u;
-    if (skip) {   // mid-block: regenerate the block and drop the draws already used
-        philox4x32_10(g.ctr0, g.ctr1, 0u, 0u, g.key0, g.key1, g.buf);
-        g.ctr1++;
-        g.have = 4u - skip;
-    }
-}
 
 template <int SHADER, int RNG_MODE, int TRIG, bool COUNT>
-__global__ void __launch_bounds__(VCRT_PBLOCK) render_persistent_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) render_persistent_kernel(const __grid_constant__ KernelArgs a) {
     const unsigned FULL = 0xffffffffu;
     const uint32_t total_items = a.owned_tiles * 1024u;
     const bool f32 = a.accum_mode == VCRT_ACCUM_F32;
@@ -83,12 +57,14 @@ __global__ void __launch_bounds__(VCRT_PBLOCK) render_persistent_kernel(const __
                     a.aov[pix] = o;
                 }
                 if (hit) {
-                    Rng g;
-                    rng_restore<RNG_MODE>(g, rng_saved, pix, a.sample_begin + k, a.philox_seed);
+                    Rng g;   // PCG: one word carried across the path; Philox: rebuilt from (pixel, sample, bounce)
+                    g.pcg = rng_saved;
+                    g.key0 = pix; g.key1 = a.philox_seed; g.ctr0 = a.sample_begin + k;
+                    rng_begin_bounce<RNG_MODE>(g, bounce);
                     float3 albedo;
                     Ray next;
                     const bool emits = scatter<SHADER, RNG_MODE, TRIG>(s, a.env, cur, rec, albedo, next, g);
-                    rng_saved = rng_save<RNG_MODE>(g);
+                    rng_saved = g.pcg;
                     cur = next;
                     thr = mul(thr, albedo);
                     bounce++;
@@ -129,9 +105,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK) render_persistent_kernel(const __
                     cur.d = normalize(pr.d);
                     thr = f3(1.0f, 1.0f, 1.0f);
                     bounce = 0;
-                    Rng g;
-                    rng_init<RNG_MODE>(g, x, y, pix, a.sample_begin + k, a.philox_seed);
-                    rng_saved = rng_save<RNG_MODE>(g);
+                    rng_saved = (600u * x + y) * (a.sample_begin + k + 1u);   // random.glsl:19 (unused by Philox)
                 }
                 trav_begin(t, s, cur);
                 st.rays++;
@@ -153,7 +127,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK) render_persistent_kernel(const __
             const bool blocked = !inner && pending != VCRT_FAST_EMPTY;   // needs the leaf phase before it can go on
             const unsigned mi = __ballot_sync(FULL, inner);
             const unsigned mb = __ballot_sync(FULL, blocked);
-            if (mb != 0u && (__popc(mb) >= VCRT_LEAF_T || mi == 0u)) {
+            if (mb != 0u && (__popc(mb) >= (int)a.leaf_threshold || mi == 0u)) {
                 if (pending != VCRT_FAST_EMPTY) {
                     if (COUNT) st.tris++;
                     trav_leaf_test(t, s, cur, pending);
@@ -167,7 +141,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK) render_persistent_kernel(const __
             }
             const bool finished = !done && t.node == VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY;
             const unsigned mf = __ballot_sync(FULL, finished);
-            if (mf != 0u && (__popc(mf) >= VCRT_SHADE_T || mi == 0u)) break;
+            if (mf != 0u && (__popc(mf) >= (int)a.shade_threshold || mi == 0u)) break;
             if (mi == 0u && mb == 0u) break;   // nothing left to traverse (only done lanes and finished ones)
         }
     }

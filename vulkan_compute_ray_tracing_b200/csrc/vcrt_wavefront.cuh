@@ -1,0 +1,217 @@
+// vcrt_wavefront.cuh -- wavefront formulation of the fast path (GPU only): ray-gen, trace and shade are separate
+// kernels that hand dense ray queues to each other through HBM.
+//
+// Why: in the megakernel (vcrt_persistent.cuh) shading runs inside the traversal warps with a handful of lanes active
+// (ncu: ~30 % of issued instructions at 2-7 active lanes), and lanes that finished a ray idle until enough of them
+// want shading.  Here
+//   trace  is a persistent-warps kernel whose lanes refill themselves from the ray queue the moment they finish
+//          (store 8 bytes, fetch an index, load 48 bytes -- cheap enough to do at low lane counts), so the hot
+//          inner-node loop keeps its lanes busy and carries no shading registers;
+//   shade  runs one thread per traced ray: all lanes active, divergence only by material;
+//   queues carry 48 B per ray: {o.xyz, path id} {d.xyz, rng word} {throughput.xyz, -}.
+// A batch is a range of work items (pixels) times ALL samples of the call; consecutive path ids are the samples of
+// one pixel.  Every finished path writes its colour to sample_color[path id]; the accumulate kernel then folds the
+// samples of a pixel in sample order, so f32 sums and rgba8 histories are bit-identical to the other kernels.
+#pragma once
+
+#include "vcrt_path.cuh"
+
+namespace vcrt {
+
+struct WfQueues {
+    float4* q[2];                 // 3 float4 per ray, two queues (ping-pong)
+    uint2* hit;                   // per ray of the current queue: {t bits, winning slot or -1}
+    float4* sample_color;         // per path of the batch: final colour (w unused)
+    unsigned int* counts;         // [0],[1]: queue sizes  [2]: trace fetch counter
+    uint32_t capacity;            // paths per batch
+};
+
+struct WfBatch {
+    uint32_t item0, nitems;       // work items (pixels) of this batch
+    uint32_t npaths;              // nitems * sample_count
+    uint32_t cur;                 // queue holding the rays of this bounce
+    uint32_t bounce;
+};
+
+__device__ __forceinline__ uint32_t wf_append_slot(unsigned int* counter, bool want) {
+    // warp-aggregated queue append: one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0u) return 0u;
+    const int leader = __ffs(m) - 1;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned base = 0u;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// ---- ray generation: one thread per path of the batch (main(), ray-trace-compute.comp:352-373, :317-319)
+template <int RNG_MODE>
+__global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
+    const uint32_t path = blockIdx.x * 256u + threadIdx.x;
+    bool valid = false;
+    uint32_t x = 0, y = 0, k = 0;
+    if (path < b.npaths) {
+        const uint32_t it = path / a.sample_count;
+        k = path - it * a.sample_count;
+        valid = item_to_pixel(a, b.item0 + it, x, y);
+    }
+    const uint32_t slot = wf_append_slot(w.counts + 0, valid);
+    if (!valid) return;
+    const Ray pr = primary_ray(a.cam, x, y);
+    const float3 d = normalize(pr.d);
+    const uint32_t rng = (600u * x + y) * (a.sample_begin + k + 1u);   // random.glsl:19 (PCG only)
+    float4* q = w.q[0] + 3 * (size_t)slot;
+    q[0] = make_float4(pr.o.x, pr.o.y, pr.o.z, u2f(path));
+    q[1] = make_float4(d.x, d.y, d.z, u2f(rng));
+    q[2] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+}
+
+// ---- trace: persistent warps, lanes refill from the queue; result = {t, slot} per ray
+template <bool COUNT>
+__global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
+    const unsigned FULL = 0xffffffffu;
+    const SceneView& s = a.scene;
+    const uint32_t count = w.counts[b.cur];
+    const float4* __restrict__ rays = w.q[b.cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(a.counters + 0, (unsigned long long)count);
+
+    bool done = false, have_ray = false;
+    uint32_t idx = 0;
+    Ray cur; cur.o = cur.d = f3(0, 0, 0);
+    TravState t;
+    t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = VCRT_FAST_EMPTY; t.sp = 0;
+    int32_t pending = VCRT_FAST_EMPTY;
+    int32_t stack[VCRT_FAST_STACK];
+    TraceStats st = {0u, 0u, 0u};
+
+    for (;;) {
+        // ---- refill: lanes whose ray is finished store the result and take the next ray
+        const bool waiting = !done && t.node == VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY;
+        if (waiting) {
+            if (have_ray) w.hit[idx] = make_uint2(f2u(t.closest), (uint32_t)t.best);
+            idx = atomicAdd(w.counts + 2, 1u);
+            have_ray = idx < count;
+            done = !have_ray;
+            if (have_ray) {
+                const float4 o = __ldg(rays + 3 * (size_t)idx), d = __ldg(rays + 3 * (size_t)idx + 1);
+                cur.o = xyz(o); cur.d = xyz(d);
+                trav_begin(t, s, cur);
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+
+        // ---- traverse until enough lanes want a refill
+        for (;;) {
+            if (t.node >= 0) {
+                if (COUNT) st.nodes++;
+                trav_inner_step(t, s, stack);
+            }
+            if (t.node < 0 && t.node != VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY) {
+                pending = t.node;
+                t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
+            }
+            const bool inner = t.node >= 0;
+            const bool blocked = !inner && pending != VCRT_FAST_EMPTY;
+            const unsigned mi = __ballot_sync(FULL, inner);
+            const unsigned mb = __ballot_sync(FULL, blocked);
+            if (mb != 0u && (__popc(mb) >= (int)a.leaf_threshold || mi == 0u)) {
+                if (pending != VCRT_FAST_EMPTY) {
+                    if (COUNT) st.tris++;
+                    trav_leaf_test(t, s, cur, pending);
+                    pending = VCRT_FAST_EMPTY;
+                    if (t.node < 0 && t.node != VCRT_FAST_EMPTY) {
+                        pending = t.node;
+                        t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
+                    }
+                }
+                continue;
+            }
+            const bool finished = !done && t.node == VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY;
+            const unsigned mf = __ballot_sync(FULL, finished);
+            if (mf != 0u && (__popc(mf) >= (int)a.shade_threshold || mi == 0u)) break;
+            if (mi == 0u && mb == 0u) break;
+        }
+    }
+    st.rays = 0u;
+    flush_stats(a, st);
+}
+
+// ---- shade: one thread per traced ray (ray_color body, ray-trace-compute.comp:321-340)
+template <int SHADER, int RNG_MODE, int TRIG>
+__global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
+    const SceneView& s = a.scene;
+    const uint32_t count = w.counts[b.cur];
+    const float4* __restrict__ rays = w.q[b.cur];
+    float4* __restrict__ next = w.q[b.cur ^ 1u];
+    for (uint32_t base = blockIdx.x * 256u; base < count; base += gridDim.x * 256u) {   // base is warp-uniform
+        const uint32_t i = base + threadIdx.x;
+        bool cont = false;
+        float4 q0, q1, q2;
+        if (i < count) {
+            q0 = rays[3 * (size_t)i]; q1 = rays[3 * (size_t)i + 1]; q2 = rays[3 * (size_t)i + 2];
+            const uint2 h = w.hit[i];
+            const uint32_t path = f2u(q0.w);
+            Ray cur; cur.o = xyz(q0); cur.d = xyz(q1);
+            float3 thr = xyz(q2);
+            TravState t;
+            t.closest = u2f(h.x); t.best = (int32_t)h.y;
+            Hit rec;
+            const bool hit = trav_finish(t, s, cur, rec);
+            const uint32_t it = path / a.sample_count, k = path - it * a.sample_count;
+            uint32_t x, y;
+            item_to_pixel(a, b.item0 + it, x, y);
+            const uint32_t pix = y * a.W + x;
+            if (b.bounce == 0 && k == 0 && (a.flags & VCRT_FLAG_WRITE_AOV)) {
+                vcrt_aov o;
+                if (hit) { o.triangle = rec.triangle; o.material = (int32_t)rec.materialIndex; o.t = rec.t; o.backFace = (uint32_t)rec.backFaceInt; }
+                else { o.triangle = -1; o.material = -1; o.t = 0.0f; o.backFace = 0u; }
+                a.aov[pix] = o;
+            }
+            if (hit) {
+                Rng g;
+                g.pcg = f2u(q1.w);
+                g.key0 = pix; g.key1 = a.philox_seed; g.ctr0 = a.sample_begin + k;
+                rng_begin_bounce<RNG_MODE>(g, b.bounce);
+                float3 albedo;
+                Ray nx;
+                const bool emits = scatter<SHADER, RNG_MODE, TRIG>(s, a.env, cur, rec, albedo, nx, g);
+                thr = mul(thr, albedo);
+                cont = !emits && (b.bounce + 1u) < a.env.max_bounces;
+                q0 = make_float4(nx.o.x, nx.o.y, nx.o.z, q0.w);
+                q1 = make_float4(nx.d.x, nx.d.y, nx.d.z, u2f(g.pcg));
+                q2 = make_float4(thr.x, thr.y, thr.z, 0.0f);
+            } else {
+                thr = scale(thr, 0.0f);
+            }
+            if (!cont) w.sample_color[path] = make_float4(thr.x, thr.y, thr.z, 1.0f);
+        }
+        const uint32_t slot = wf_append_slot(w.counts + (b.cur ^ 1u), cont);
+        if (cont) {
+            float4* q = next + 3 * (size_t)slot;
+            q[0] = q0; q[1] = q1; q[2] = q2;
+        }
+    }
+}
+
+// ---- accumulate: one thread per work item, samples folded in order (ray-trace-compute.comp:375-379)
+__global__ void __launch_bounds__(256) wf_accumulate_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
+    const uint32_t it = blockIdx.x * 256u + threadIdx.x;
+    if (it >= b.nitems) return;
+    uint32_t x, y;
+    if (!item_to_pixel(a, b.item0 + it, x, y)) return;
+    const uint32_t pix = y * a.W + x;
+    const float4* c = w.sample_color + (size_t)it * a.sample_count;
+    if (a.accum_mode == VCRT_ACCUM_F32) {
+        float4 acc = a.accumf[pix];
+        for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = c[k]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += 1.0f; }
+        a.accumf[pix] = acc;
+    } else {
+        uchar4 px = a.accum8[pix];
+        for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = c[k]; running_mean_rgba8(px, f3(v.x, v.y, v.z), a.sample_begin + k); }
+        a.target[pix] = px;
+        a.accum8[pix] = px;
+    }
+}
+
+}  // namespace vcrt
