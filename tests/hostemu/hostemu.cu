@@ -54,6 +54,12 @@ extern "C" int hostemu_render(const void* tris, uint32_t ntris, const void* mats
             return -1;
         }
         s.fnodes = (const float4*)fb.nodes.data(); s.ftris = (const float4*)fb.tris.data(); s.nfnodes = fb.num_nodes(); s.froot = fb.root;
+        // test hooks: _reserved bit 1 keeps the 64-byte float nodes, bit 2 quantises whatever the scene extent
+        if (!(p->_reserved & 2u) && quantize_fast_bvh(fb, (p->_reserved & 4u) ? 3.0e38f : 2.5e-4f)) {
+            s.qnodes = (const Words8*)fb.qnodes.data();   // std::vector storage is 16-byte aligned; the host load is a plain copy
+            s.qorg = make_float3(fb.qorg[0], fb.qorg[1], fb.qorg[2]);
+            s.qext = make_float3(fb.qext[0], fb.qext[1], fb.qext[2]);
+        }
     }
     const bool ref_cov = (p->flags & VCRT_FLAG_REF_DISPATCH_COVERAGE) != 0;
     setup_args(a, *ubo, *p, W, H, ref_cov ? (W / 32) * 32 : W, ref_cov ? (H / 32) * 32 : H, nlights);

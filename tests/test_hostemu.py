@@ -70,3 +70,34 @@ def test_repack_rejects_unsupported_trees(hostemu):
     sc["bvh"] = nodes.view(np.uint8).reshape(-1)
     with pytest.raises(RuntimeError, match="reachable twice"):
         hostemu.render(sc, (0.0, 6.0, 1.5), 32, 32, make_params(traversal="fast"))
+
+
+@pytest.mark.parametrize("fmt", ["auto", "f32", "q15_forced"])
+def test_node_formats_give_identical_results(oracle, hostemu, doge, fmt):
+    """32-byte quantised nodes (one 256-bit load per visit) vs 64-byte float nodes: boxes only cull, so every output
+    bit is the same; the quantised tree may only visit MORE nodes.  `q15_forced` also runs a scene 1000x larger than the
+    quantiser's automatic limit (coarse quanta: correctness must not depend on them)."""
+    reserved = {"auto": 0, "f32": 2, "q15_forced": 4}[fmt]
+    cases = [(doge, CAM, 160, 120), (small_scene(n_tris=3000, seed=11), (0.0, 6.0, 1.5), 96, 64)]
+    if fmt == "q15_forced":
+        big = small_scene(n_tris=800, seed=12)
+        big = dict(big)
+        t = big["triangles"].copy().view(np.float32).reshape(-1, 12)
+        t[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]] *= 1000.0
+        big["triangles"] = t.view(np.uint8).reshape(-1)
+        import tinybvh
+        big["bvh"] = tinybvh.build_bvh(big["triangles"].view(tinybvh.TRI), seed=2).view(np.uint8).reshape(-1).copy()
+        cases.append((big, (0.0, 6000.0, 1500.0), 96, 64))
+    for sc, cam, w, h in cases:
+        kw = dict(shader="full", max_bounces=5, sample_count=2, accum="f32", rng="philox", stack_depth=64)
+        a = oracle.render(sc, cam, w, h, make_params(traversal="reference", **kw), want_aov=True)
+        p = make_params(traversal="fast", **kw)
+        p._reserved = reserved
+        b = hostemu.render(sc, cam, w, h, p, want_aov=True)
+        assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"])
+        pf = make_params(traversal="fast", **kw)
+        pf._reserved = 2
+        f = hostemu.render(sc, cam, w, h, pf, want_aov=True)
+        assert b["nodes"] >= f["nodes"] and b["rays"] == f["rays"]
+        if fmt != "f32" and sc is doge:
+            assert b["nodes"] <= 1.1 * f["nodes"]        # quantisation costs only a few per cent more visits here

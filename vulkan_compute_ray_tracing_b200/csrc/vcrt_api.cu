@@ -33,6 +33,10 @@ struct vcrt_ctx {
     bool fast_dirty = true;
     uint32_t leaf_threshold = 3, shade_threshold = 10;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
     bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
+    int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (quantised when the scene extent allows) | 1 "q15" | 2 "f32"
+    bool quantized = false;
+    float qorg[3] = {0, 0, 0}, qext[3] = {0, 0, 0};
+    DevBuf qnodes;
     bool fast_ok = false;
     std::string fast_err;
     DevBuf fnodes, ftris;
@@ -118,6 +122,12 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         if (sah != c->fast_sah) { c->fast_sah = sah; c->fast_dirty = true; }
         return VCRT_OK;
     }
+    if (k == "fast_nodes") {
+        const int m = v == "auto" ? 0 : v == "q15" ? 1 : v == "f32" ? 2 : -1;
+        if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: fast_nodes must be 'auto', 'q15' or 'f32'");
+        if (m != c->fast_nodes) { c->fast_nodes = m; c->fast_dirty = true; }
+        return VCRT_OK;
+    }
     if (k == "leaf_threshold" || k == "shade_threshold") {
         const int n = atoi(value);
         if (n < 1 || n > 32) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: threshold must be 1..32 lanes");
@@ -141,7 +151,7 @@ int vcrt_destroy(vcrt_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
-    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts}) if (b->ptr) cudaFree(b->ptr);
+    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes}) if (b->ptr) cudaFree(b->ptr);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -230,6 +240,14 @@ static int prepare_fast(vcrt_ctx* c) {
             if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris.size() * 4, "allocate repacked triangles"))) return rc;
             if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
             if (!fb.tris.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris.data(), fb.tris.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
+            // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
+            c->quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, c->fast_nodes == 1 ? 3.0e38f : 2.5e-4f);
+            if (c->quantized) {
+                if ((rc = ensure(c, c->qnodes, fb.qnodes.size() * 4, "allocate quantised nodes"))) return rc;
+                CU(c, cudaMemcpyAsync(c->qnodes.ptr, fb.qnodes.data(), fb.qnodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload quantised nodes");
+                std::memcpy(c->qorg, fb.qorg, sizeof c->qorg);
+                std::memcpy(c->qext, fb.qext, sizeof c->qext);
+            }
             CU(c, cudaStreamSynchronize(c->stream), "synchronize");
             c->froot = fb.root;
             c->nfnodes = fb.num_nodes();
@@ -260,6 +278,11 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
         int rc = prepare_fast(c);
         if (rc) return rc;
         s.fnodes = (const float4*)c->fnodes.ptr; s.ftris = (const float4*)c->ftris.ptr; s.nfnodes = c->nfnodes; s.froot = c->froot;
+        if (c->quantized) {
+            s.qnodes = (const Words8*)c->qnodes.ptr;
+            s.qorg = make_float3(c->qorg[0], c->qorg[1], c->qorg[2]);
+            s.qext = make_float3(c->qext[0], c->qext[1], c->qext[2]);
+        }
     } else {
         s.froot = (int32_t)0x80000000;
     }

@@ -65,6 +65,39 @@ VCRT_HD float4 ldg4(const float4* p) {
 #endif
 }
 
+// One 256-bit read-only load (LDG.E.256 on sm_100a): a divergent lane costs one L1 data-pipe wavefront per 32-byte
+// sector it touches, so 32 bytes per instruction halves the wavefronts of two 128-bit loads.  p must be 32-byte aligned.
+struct __align__(32) Words8 { uint32_t w[8]; };
+VCRT_HD Words8 ldg8(const Words8* p) {
+#ifdef __CUDA_ARCH__
+    Words8 r;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+#else
+    Words8 r;   // host emulation: the source may be only 4-byte aligned
+    for (int i = 0; i < 8; ++i) r.w[i] = ((const uint32_t*)p)[i];
+    return r;
+#endif
+}
+
+// 15-bit fixed point -> float m = 0.5 * (1 + q / 32768) in [0.5, 1), exactly, in one PRMT: the 16-bit field becomes
+// bits 8..23 of a float whose exponent byte is 0x3F (bit 23 = the field's top bit = 0).
+VCRT_HD float q15_lo(uint32_t w) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104));
+#else
+    return u2f(0x3F000000u | ((w & 0xffffu) << 8));
+#endif
+}
+VCRT_HD float q15_hi(uint32_t w) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324));
+#else
+    return u2f(0x3F000000u | ((w >> 16) << 8));
+#endif
+}
+
 // ------------------------------------------------------------------------------------------ trig
 // VCRT_TRIG_PORTABLE: fixed fp32 sequence, bit-identical to the oracle's (no FMA, IEEE ops only).
 VCRT_HD void sincos_portable(float x, float* s, float* c) {
@@ -167,6 +200,9 @@ struct SceneView {
     const float4* ftris;    // 48 B per triangle, leaf order
     uint32_t nfnodes;
     int32_t froot;          // >= 0 inner node, < 0 leaf (~triangle slot), INT_MIN empty
+    // 32-byte quantised inner nodes (vcrt_repack.h: quantize_fast_bvh); null = walk the 64-byte float nodes
+    const Words8* qnodes;
+    float3 qorg, qext;      // coordinate = qorg + 2m * qext
 };
 
 struct Ray { float3 o, d; };

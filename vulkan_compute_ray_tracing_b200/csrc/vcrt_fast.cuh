@@ -14,6 +14,9 @@
 //                      {L.min.z L.max.z R.min.z R.max.z} {childL childR - -}
 //                      child >= 0: inner node index;  child < 0: leaf, triangle slot = ~child;  empty: box (+inf,-inf)
 //   triangle, 48 B:    {v0.xyz, original index} {v1.xyz, materialIndex} {v2.xyz, -}   in reference DFS leaf order
+//   quantised inner node, 32 B (QN = 1; used when the scene extent allows, vcrt_repack.h): the same twelve bounds as
+//                      15-bit fixed point in a scene-wide frame, rounded outwards, + the two child codes; one 256-bit load.
+//                      Boxes only grow, so the visited set is a superset of the float nodes' and results are unchanged.
 #pragma once
 
 #include "vcrt_core.cuh"
@@ -29,19 +32,26 @@ VCRT_HD float fmax_(float a, float b) { return fmaxf(a, b); }
 // Per-ray traversal state, advanced one node at a time so that the persistent kernel (vcrt_persistent.cuh) can
 // interleave the rays of a warp; hit_bvh_fast below runs the same steps to completion for one ray.
 struct TravState {
-    float3 idir, ood;       // 1/d (guarded) and o/d for the fma slab test
+    float3 idir, ood;       // 1/d (guarded) and o/d for the fma slab test; quantised nodes: 2*qext/d and (o - qorg)/d
     float closest;
     int32_t best;           // winning triangle slot or -1
     int32_t node;           // >= 0 inner node to visit, < 0 leaf (~slot), VCRT_FAST_EMPTY: nothing left
     int sp;
 };
 
+template <int QN>
 VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
     const float tiny = 1e-30f;   // guard so that 0 * inf never appears
     t.idir = f3(1.0f / (fabsf(r.d.x) > tiny ? r.d.x : copysignf(tiny, r.d.x)),
                 1.0f / (fabsf(r.d.y) > tiny ? r.d.y : copysignf(tiny, r.d.y)),
                 1.0f / (fabsf(r.d.z) > tiny ? r.d.z : copysignf(tiny, r.d.z)));
-    t.ood = f3(r.o.x * t.idir.x, r.o.y * t.idir.y, r.o.z * t.idir.z);
+    if (QN) {
+        // t(bound) = (qorg + 2m*qext - o) / d = m * (2*qext/d) - (o - qorg)/d
+        t.ood = f3((r.o.x - s.qorg.x) * t.idir.x, (r.o.y - s.qorg.y) * t.idir.y, (r.o.z - s.qorg.z) * t.idir.z);
+        t.idir = f3(2.0f * s.qext.x * t.idir.x, 2.0f * s.qext.y * t.idir.y, 2.0f * s.qext.z * t.idir.z);
+    } else {
+        t.ood = f3(r.o.x * t.idir.x, r.o.y * t.idir.y, r.o.z * t.idir.z);
+    }
     t.closest = VCRT_T_MAX;
     t.best = -1;
     t.node = s.froot;
@@ -49,22 +59,36 @@ VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
 }
 
 // Visit inner node t.node: test both children, descend into the nearer hit child, push the farther one.
+template <int QN>
 VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
-    const float4* p = s.fnodes + 4 * (size_t)t.node;
-    const float4 n0 = ldg4(p), n1 = ldg4(p + 1), n2 = ldg4(p + 2), n3 = ldg4(p + 3);
-    const float lx0 = fmaf(n0.x, t.idir.x, -t.ood.x), lx1 = fmaf(n0.y, t.idir.x, -t.ood.x);
-    const float ly0 = fmaf(n0.z, t.idir.y, -t.ood.y), ly1 = fmaf(n0.w, t.idir.y, -t.ood.y);
-    const float lz0 = fmaf(n2.x, t.idir.z, -t.ood.z), lz1 = fmaf(n2.y, t.idir.z, -t.ood.z);
-    const float rx0 = fmaf(n1.x, t.idir.x, -t.ood.x), rx1 = fmaf(n1.y, t.idir.x, -t.ood.x);
-    const float ry0 = fmaf(n1.z, t.idir.y, -t.ood.y), ry1 = fmaf(n1.w, t.idir.y, -t.ood.y);
-    const float rz0 = fmaf(n2.z, t.idir.z, -t.ood.z), rz1 = fmaf(n2.w, t.idir.z, -t.ood.z);
+    float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
+    int32_t cl, cr;
+    if (QN) {
+        const Words8 n = ldg8(s.qnodes + t.node);
+        lx0 = fmaf(q15_lo(n.w[0]), t.idir.x, -t.ood.x); lx1 = fmaf(q15_hi(n.w[0]), t.idir.x, -t.ood.x);
+        ly0 = fmaf(q15_lo(n.w[1]), t.idir.y, -t.ood.y); ly1 = fmaf(q15_hi(n.w[1]), t.idir.y, -t.ood.y);
+        lz0 = fmaf(q15_lo(n.w[2]), t.idir.z, -t.ood.z); lz1 = fmaf(q15_hi(n.w[2]), t.idir.z, -t.ood.z);
+        rx0 = fmaf(q15_lo(n.w[3]), t.idir.x, -t.ood.x); rx1 = fmaf(q15_hi(n.w[3]), t.idir.x, -t.ood.x);
+        ry0 = fmaf(q15_lo(n.w[4]), t.idir.y, -t.ood.y); ry1 = fmaf(q15_hi(n.w[4]), t.idir.y, -t.ood.y);
+        rz0 = fmaf(q15_lo(n.w[5]), t.idir.z, -t.ood.z); rz1 = fmaf(q15_hi(n.w[5]), t.idir.z, -t.ood.z);
+        cl = (int32_t)n.w[6]; cr = (int32_t)n.w[7];
+    } else {
+        const float4* p = s.fnodes + 4 * (size_t)t.node;
+        const float4 n0 = ldg4(p), n1 = ldg4(p + 1), n2 = ldg4(p + 2), n3 = ldg4(p + 3);
+        lx0 = fmaf(n0.x, t.idir.x, -t.ood.x); lx1 = fmaf(n0.y, t.idir.x, -t.ood.x);
+        ly0 = fmaf(n0.z, t.idir.y, -t.ood.y); ly1 = fmaf(n0.w, t.idir.y, -t.ood.y);
+        lz0 = fmaf(n2.x, t.idir.z, -t.ood.z); lz1 = fmaf(n2.y, t.idir.z, -t.ood.z);
+        rx0 = fmaf(n1.x, t.idir.x, -t.ood.x); rx1 = fmaf(n1.y, t.idir.x, -t.ood.x);
+        ry0 = fmaf(n1.z, t.idir.y, -t.ood.y); ry1 = fmaf(n1.w, t.idir.y, -t.ood.y);
+        rz0 = fmaf(n2.z, t.idir.z, -t.ood.z); rz1 = fmaf(n2.w, t.idir.z, -t.ood.z);
+        cl = (int32_t)f2u(n3.x); cr = (int32_t)f2u(n3.y);
+    }
     const float lN = fmax_(fmax_(fmin_(lx0, lx1), fmin_(ly0, ly1)), fmax_(fmin_(lz0, lz1), 0.0f));
     const float lF = fmin_(fmin_(fmax_(lx0, lx1), fmax_(ly0, ly1)), fmax_(lz0, lz1)) * 1.0000004f;
     const float rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
     const float rF = fmin_(fmin_(fmax_(rx0, rx1), fmax_(ry0, ry1)), fmax_(rz0, rz1)) * 1.0000004f;
     const bool hl = lN <= fmin_(lF, t.closest);
     const bool hr = rN <= fmin_(rF, t.closest);
-    const int32_t cl = (int32_t)f2u(n3.x), cr = (int32_t)f2u(n3.y);
     if (hl && hr) {
         const bool left_first = lN <= rN;
         t.node = left_first ? cl : cr;
@@ -98,15 +122,15 @@ VCRT_HD bool trav_finish(const TravState& t, const SceneView& s, const Ray& r, H
     return true;
 }
 
-template <bool COUNT>
-VCRT_HD bool hit_bvh_fast(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
+template <bool COUNT, int QN>
+VCRT_HD bool hit_bvh_fast_q(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
     TravState t;
-    trav_begin(t, s, r);
+    trav_begin<QN>(t, s, r);
     int32_t stack[VCRT_FAST_STACK];
     while (t.node != VCRT_FAST_EMPTY) {
         if (t.node >= 0) {
             if (COUNT) st.nodes++;
-            trav_inner_step(t, s, stack);
+            trav_inner_step<QN>(t, s, stack);
         } else {
             if (COUNT) st.tris++;
             trav_leaf_test(t, s, r, t.node);
@@ -114,6 +138,11 @@ VCRT_HD bool hit_bvh_fast(const SceneView& s, const Ray& r, Hit& rec, TraceStats
         }
     }
     return trav_finish(t, s, r, rec);
+}
+
+template <bool COUNT>
+VCRT_HD bool hit_bvh_fast(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
+    return s.qnodes ? hit_bvh_fast_q<COUNT, 1>(s, r, rec, st) : hit_bvh_fast_q<COUNT, 0>(s, r, rec, st);
 }
 
 }  // namespace vcrt

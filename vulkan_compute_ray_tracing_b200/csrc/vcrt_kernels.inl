@@ -102,16 +102,21 @@ __global__ void wf_reset_kernel(unsigned int* counts, int which) {
 
 template <int SHADER, int RNG_MODE, int TRIG>
 static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
-    static int trace_grid[2] = {0, 0}, sms = 0;
+    // the four trace variants: [COUNT][QN]
+    typedef void (*TraceFn)(const KernelArgs, const WfQueues, const WfBatch);
+    static const TraceFn trace_fn[2][2] = {{wf_trace_kernel<false, 0>, wf_trace_kernel<false, 1>}, {wf_trace_kernel<true, 0>, wf_trace_kernel<true, 1>}};
+    static int trace_grid[2][2] = {{0, 0}, {0, 0}}, sms = 0;
     if (sms == 0) {
         int dev = 0, per_sm = 0;
         cudaError_t e;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<false>, VCRT_PBLOCK, 0)) != cudaSuccess) return e;
-        trace_grid[0] = sms * (per_sm > 0 ? per_sm : 1);
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<true>, VCRT_PBLOCK, 0)) != cudaSuccess) return e;
-        trace_grid[1] = sms * (per_sm > 0 ? per_sm : 1);
+        for (int c = 0; c < 2; ++c)
+            for (int q = 0; q < 2; ++q) {
+                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_fn[c][q], VCRT_PBLOCK, 0)) != cudaSuccess) return e;
+                trace_grid[c][q] = sms * (per_sm > 0 ? per_sm : 1);
+            }
     }
+    const int ci = count ? 1 : 0, qi = a.scene.qnodes ? 1 : 0;
     const uint32_t items = a.owned_tiles * 1024u;
     const uint32_t per_batch = w.capacity / a.sample_count;   // capacity >= sample_count is guaranteed by the caller
     const uint32_t shade_grid = (uint32_t)sms * 8u;
@@ -128,8 +133,7 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, 
         for (uint32_t bounce = 0; bounce < a.env.max_bounces; ++bounce) {
             b.bounce = bounce;
             wf_reset_kernel<<<1, 1, 0, stream>>>(w.counts, (int)(b.cur ^ 1u));
-            if (count) wf_trace_kernel<true><<<trace_grid[1], VCRT_PBLOCK, 0, stream>>>(a, w, b);
-            else wf_trace_kernel<false><<<trace_grid[0], VCRT_PBLOCK, 0, stream>>>(a, w, b);
+            trace_fn[ci][qi]<<<trace_grid[ci][qi], VCRT_PBLOCK, 0, stream>>>(a, w, b);
             wf_shade_kernel<SHADER, RNG_MODE, TRIG><<<shade_grid, 256, 0, stream>>>(a, w, b);
             *launches += 3;
             b.cur ^= 1u;

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) render_persistent_ker
     const uint32_t total_items = a.owned_tiles * 1024u;
     const bool f32 = a.accum_mode == VCRT_ACCUM_F32;
     const SceneView& s = a.scene;
+    const bool qn = s.qnodes != nullptr;   // uniform: quantised 32-byte nodes or 64-byte float nodes
 
     // ---- lane state
     bool has_pixel = false, done = false;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) render_persistent_ker
                     bounce = 0;
                     rng_saved = (600u * x + y) * (a.sample_begin + k + 1u);   // random.glsl:19 (unused by Philox)
                 }
-                trav_begin(t, s, cur);
+                if (qn) trav_begin<1>(t, s, cur); else trav_begin<0>(t, s, cur);
                 st.rays++;
             }
         }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) render_persistent_ker
         for (;;) {
             if (t.node >= 0) {
                 if (COUNT) st.nodes++;
-                trav_inner_step(t, s, stack);
+                if (qn) trav_inner_step<1>(t, s, stack); else trav_inner_step<0>(t, s, stack);
             }
             if (t.node < 0 && t.node != VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY) {   // postpone one leaf, keep going
                 pending = t.node;

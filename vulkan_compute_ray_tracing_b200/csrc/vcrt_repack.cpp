@@ -208,4 +208,65 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err) {
     return true;
 }
 
+// ------------------------------------------------------------------------------------------ quantisation
+bool quantize_fast_bvh(FastBvh& fb, float max_quantum) {
+    fb.qnodes.clear();
+    const uint32_t n = fb.num_nodes();
+    if (n == 0) return false;
+    const double inf = std::numeric_limits<double>::infinity();
+    double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    // word index of {min, max} per child and axis in the 64-byte record (layout: vcrt_fast.cuh)
+    static const int kMin[2][3] = {{0, 2, 8}, {4, 6, 10}};
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* p = &fb.nodes[(size_t)i * 16];
+        for (int c = 0; c < 2; ++c)
+            for (int a = 0; a < 3; ++a) {
+                const double mn = p[kMin[c][a]], mx = p[kMin[c][a] + 1];
+                if (!(mn <= mx)) continue;               // empty child (+inf, -inf)
+                if (!std::isfinite(mn) || !std::isfinite(mx)) return false;
+                lo[a] = std::min(lo[a], mn); hi[a] = std::max(hi[a], mx);
+            }
+    }
+    double quantum[3], base[3];
+    for (int a = 0; a < 3; ++a) {
+        if (!(lo[a] <= hi[a])) return false;             // no finite box at all
+        double ext = hi[a] - lo[a];
+        if (!(ext > 0.0)) ext = 1e-3;                    // flat scene on this axis
+        quantum[a] = ext / 32764.0;                      // q stays inside [1, 32766]
+        base[a] = lo[a] - quantum[a];
+        if (quantum[a] > (double)max_quantum) return false;
+    }
+    for (int a = 0; a < 3; ++a) {
+        const double E = 32768.0 * quantum[a];
+        fb.qorg[a] = (float)(base[a] - E);
+        fb.qext[a] = (float)E;
+        // the kernel decodes with these rounded floats; make sure rounding did not move the frame by a visible amount
+        if (std::fabs((double)fb.qorg[a] - (base[a] - E)) > 0.01 * quantum[a] || std::fabs((double)fb.qext[a] - E) > 1e-6 * E) return false;
+    }
+    fb.qnodes.resize((size_t)n * 8);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        const float* p = &fb.nodes[(size_t)i * 16];
+        uint32_t* q = &fb.qnodes[(size_t)i * 8];
+        for (int c = 0; c < 2; ++c)
+            for (int a = 0; a < 3; ++a) {
+                const double mn = p[kMin[c][a]], mx = p[kMin[c][a] + 1];
+                uint32_t qlo = 32767u, qhi = 0u;         // empty child: min > max on every axis, never entered
+                if (mn <= mx) {
+                    // decoded value = qorg + (1 + q/32768) * qext, evaluated with the floats the kernel uses
+                    const double org = fb.qorg[a], ext = fb.qext[a];
+                    double l = std::floor((mn - org - ext) / ext * 32768.0), h = std::ceil((mx - org - ext) / ext * 32768.0);
+                    while (l > 0.0 && org + (1.0 + l / 32768.0) * ext > mn) l -= 1.0;
+                    while (h < 32767.0 && org + (1.0 + h / 32768.0) * ext < mx) h += 1.0;
+                    qlo = (uint32_t)std::min(std::max(l, 0.0), 32767.0);
+                    qhi = (uint32_t)std::min(std::max(h, 0.0), 32767.0);
+                }
+                q[c * 3 + a] = qlo | (qhi << 16);
+            }
+        std::memcpy(&q[6], &p[12], 4);
+        std::memcpy(&q[7], &p[13], 4);
+    }
+    return true;
+}
+
 }  // namespace vcrt

@@ -10,6 +10,9 @@ namespace vcrt {
 struct FastBvh {
     std::vector<float> nodes;      // 16 floats per inner node
     std::vector<float> tris;       // 12 floats per triangle slot
+    std::vector<uint32_t> qnodes;  // 8 words per inner node (quantised form of `nodes`, see quantize_fast_bvh); empty = not quantised
+    float qorg[3] = {0, 0, 0};     // decode frame: coordinate = qorg + (2m) * qext, m = 0.5 * (1 + q / 32768) in [0.5, 1)
+    float qext[3] = {0, 0, 0};
     int32_t root = (int32_t)0x80000000;
     uint32_t depth = 0;            // deepest leaf (root = 0)
     uint32_t num_nodes() const { return (uint32_t)(nodes.size() / 16); }
@@ -26,5 +29,14 @@ bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle
 // visits does).  The reference's builder splits at the median of a random axis (Bvh.h:160,175), which costs several
 // times more node visits per ray than a surface-area-heuristic tree.  Parallel over subtrees (OpenMP tasks).
 bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err);
+
+// 32-byte form of the inner nodes: the twelve child-box bounds as 15-bit fixed point in one scene-wide frame, rounded
+// outwards (boxes only grow, so culling stays conservative and results do not change), followed by the two child codes:
+//   {Lx0|Lx1<<16, Ly0|Ly1<<16, Lz0|Lz1<<16, Rx0|Rx1<<16, Ry0|Ry1<<16, Rz0|Rz1<<16, childL, childR}
+// One 256-bit load per visit instead of four 128-bit ones (the trace kernel is bound by L1 data-pipe wavefronts,
+// DESIGN.md section 6).  Done only when the quantum (scene extent / 32766) is at most `max_quantum` on every axis --
+// the reference pads every leaf box by 1e-4 (Bvh.h:16), so quanta of that order cost a few per cent more triangle tests;
+// beyond that the 64-byte float nodes are kept.  Returns whether the quantised form was produced.
+bool quantize_fast_bvh(FastBvh& fb, float max_quantum);
 
 }  // namespace vcrt

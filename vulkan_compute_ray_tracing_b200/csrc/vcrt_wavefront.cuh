@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant_
 }
 
 // ---- trace: persistent warps, lanes refill from the queue; result = {t, slot} per ray
-template <bool COUNT>
+template <bool COUNT, int QN>
 __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
     const unsigned FULL = 0xffffffffu;
     const SceneView& s = a.scene;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             if (have_ray) {
                 const float4 o = __ldg(rays + 3 * (size_t)idx), d = __ldg(rays + 3 * (size_t)idx + 1);
                 cur.o = xyz(o); cur.d = xyz(d);
-                trav_begin(t, s, cur);
+                trav_begin<QN>(t, s, cur);
             }
         }
         if (__all_sync(FULL, done)) break;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
         for (;;) {
             if (t.node >= 0) {
                 if (COUNT) st.nodes++;
-                trav_inner_step(t, s, stack);
+                trav_inner_step<QN>(t, s, stack);
             }
             if (t.node < 0 && t.node != VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY) {
                 pending = t.node;
