@@ -31,7 +31,7 @@ struct vcrt_ctx {
     DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
     std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
     bool fast_dirty = true;
-    uint32_t leaf_threshold = 3, shade_threshold = 10;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
+    uint32_t leaf_threshold = 4, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
     bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
     int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (quantised when the scene extent allows) | 1 "q15" | 2 "f32"
     bool quantized = false;
@@ -42,6 +42,7 @@ struct vcrt_ctx {
     DevBuf fnodes, ftris;
     DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues
     uint32_t wf_capacity = 0;
+    uint32_t wf_batch = 32u << 20;         // option "wf_batch_paths": paths per wavefront batch (queue memory = 120 B per path)
     int32_t froot = (int32_t)0x80000000;
     uint32_t nfnodes = 0;
     uint32_t W = 0, H = 0;
@@ -126,6 +127,12 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         const int m = v == "auto" ? 0 : v == "q15" ? 1 : v == "f32" ? 2 : -1;
         if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: fast_nodes must be 'auto', 'q15' or 'f32'");
         if (m != c->fast_nodes) { c->fast_nodes = m; c->fast_dirty = true; }
+        return VCRT_OK;
+    }
+    if (k == "wf_batch_paths") {
+        const long long n = atoll(value);
+        if (n < 1024 || n > (1ll << 30)) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: wf_batch_paths must be 1024..2^30");
+        c->wf_batch = (uint32_t)n;
         return VCRT_OK;
     }
     if (k == "leaf_threshold" || k == "shade_threshold") {
@@ -303,8 +310,12 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     uint32_t nlaunch = 1;
     if (p.traversal == VCRT_TRAVERSAL_FAST && !(p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL))) {
         // wavefront pipeline: queues sized for a batch of paths (a range of pixels x all samples of the call)
-        const uint32_t want = a.sample_count > (8u << 20) ? a.sample_count : (8u << 20);
-        if (c->wf_capacity < want) {
+        // batch = as many whole pixels (all samples of the call) as fit wf_batch paths, but no more than the call needs
+        const uint64_t need = (uint64_t)a.owned_tiles * 1024u * a.sample_count;
+        uint32_t want = (uint32_t)(need < c->wf_batch ? need : c->wf_batch);
+        if (want < a.sample_count) want = a.sample_count;
+        if (want < 1024u) want = 1024u;
+        if (c->wf_capacity != want) {
             int rc;
             if ((rc = ensure(c, c->wf_q0, (size_t)want * 48, "allocate ray queue")) || (rc = ensure(c, c->wf_q1, (size_t)want * 48, "allocate ray queue")) ||
                 (rc = ensure(c, c->wf_hit, (size_t)want * 8, "allocate hit buffer")) || (rc = ensure(c, c->wf_color, (size_t)want * 16, "allocate sample buffer")) ||

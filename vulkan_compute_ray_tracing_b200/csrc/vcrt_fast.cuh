@@ -58,11 +58,10 @@ VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
     t.sp = 0;
 }
 
-// Visit inner node t.node: test both children, descend into the nearer hit child, push the farther one.
+// Both children of inner node t.node against the ray: entry distances (clamped to 0), hit verdicts and child codes.
 template <int QN>
-VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
+VCRT_HD void trav_test_children(const TravState& t, const SceneView& s, float& lN, float& rN, bool& hl, bool& hr, int32_t& cl, int32_t& cr) {
     float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
-    int32_t cl, cr;
     if (QN) {
         const Words8 n = ldg8(s.qnodes + t.node);
         lx0 = fmaf(q15_lo(n.w[0]), t.idir.x, -t.ood.x); lx1 = fmaf(q15_hi(n.w[0]), t.idir.x, -t.ood.x);
@@ -83,12 +82,21 @@ VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
         rz0 = fmaf(n2.z, t.idir.z, -t.ood.z); rz1 = fmaf(n2.w, t.idir.z, -t.ood.z);
         cl = (int32_t)f2u(n3.x); cr = (int32_t)f2u(n3.y);
     }
-    const float lN = fmax_(fmax_(fmin_(lx0, lx1), fmin_(ly0, ly1)), fmax_(fmin_(lz0, lz1), 0.0f));
+    lN = fmax_(fmax_(fmin_(lx0, lx1), fmin_(ly0, ly1)), fmax_(fmin_(lz0, lz1), 0.0f));
     const float lF = fmin_(fmin_(fmax_(lx0, lx1), fmax_(ly0, ly1)), fmax_(lz0, lz1)) * 1.0000004f;
-    const float rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
+    rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
     const float rF = fmin_(fmin_(fmax_(rx0, rx1), fmax_(ry0, ry1)), fmax_(rz0, rz1)) * 1.0000004f;
-    const bool hl = lN <= fmin_(lF, t.closest);
-    const bool hr = rN <= fmin_(rF, t.closest);
+    hl = lN <= fmin_(lF, t.closest);
+    hr = rN <= fmin_(rF, t.closest);
+}
+
+// Visit inner node t.node: test both children, descend into the nearer hit child, push the farther one.
+template <int QN>
+VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
+    float lN, rN;
+    bool hl, hr;
+    int32_t cl, cr;
+    trav_test_children<QN>(t, s, lN, rN, hl, hr, cl, cr);
     if (hl && hr) {
         const bool left_first = lN <= rN;
         t.node = left_first ? cl : cr;
@@ -100,6 +108,24 @@ VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
     } else {
         t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
     }
+}
+
+// The same visit for the wavefront trace kernel, written for predication instead of branches: the stack holds the
+// sentinel VCRT_FAST_EMPTY at index 0 (t.sp starts at 1), so "pop" is unconditional and an exhausted stack yields EMPTY
+// without a test; depth never exceeds the stack (vcrt_repack.cpp rejects deeper trees), so "push" needs no bound check.
+template <int QN>
+VCRT_HD void trav_inner_step_lean(TravState& t, const SceneView& s, int32_t* stack) {
+    float lN, rN;
+    bool hl, hr;
+    int32_t cl, cr;
+    trav_test_children<QN>(t, s, lN, rN, hl, hr, cl, cr);
+    const bool left_first = hl && (!hr || lN <= rN);
+    const int32_t near_c = left_first ? cl : cr, far_c = left_first ? cr : cl;
+    const bool both = hl && hr, none = !(hl || hr);
+    if (both) stack[t.sp] = far_c;
+    t.sp += both ? 1 : 0;
+    t.sp -= none ? 1 : 0;
+    t.node = none ? stack[t.sp] : near_c;
 }
 
 // Test the triangle of leaf code `leaf` (= ~slot) with the reference's arithmetic and tie rule.

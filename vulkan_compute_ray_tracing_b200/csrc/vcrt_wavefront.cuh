@@ -68,69 +68,78 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant_
 }
 
 // ---- trace: persistent warps, lanes refill from the queue; result = {t, slot} per ray
+// Lane state: t.node (inner node >= 0 | leaf code < 0 | EMPTY), one postponed leaf, the stack with its sentinel.  The
+// loop body is written for predication (trav_inner_step_lean): ncu on the branchy version showed ~50 of ~110 warp
+// instructions per iteration spent on control flow around the 57-instruction box test (profiles/r01_v4_*).
 template <bool COUNT, int QN>
 __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
     const unsigned FULL = 0xffffffffu;
+    const int32_t EMPTY = VCRT_FAST_EMPTY;
     const SceneView& s = a.scene;
     const uint32_t count = w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
     if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(a.counters + 0, (unsigned long long)count);
+    const int leaf_t = (int)a.leaf_threshold, refill_t = (int)a.shade_threshold;
 
-    bool done = false, have_ray = false;
-    uint32_t idx = 0;
+    uint32_t idx = 0xffffffffu;          // ray in flight (0xffffffff: none)
+    bool done = false;                   // the queue is exhausted for this lane
     Ray cur; cur.o = cur.d = f3(0, 0, 0);
     TravState t;
-    t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = VCRT_FAST_EMPTY; t.sp = 0;
-    int32_t pending = VCRT_FAST_EMPTY;
+    t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = EMPTY; t.sp = 0;
+    int32_t pending = EMPTY;
     int32_t stack[VCRT_FAST_STACK];
+    stack[0] = EMPTY;                    // sentinel: popping an exhausted stack yields EMPTY
     TraceStats st = {0u, 0u, 0u};
 
     for (;;) {
         // ---- refill: lanes whose ray is finished store the result and take the next ray
-        const bool waiting = !done && t.node == VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY;
-        if (waiting) {
-            if (have_ray) w.hit[idx] = make_uint2(f2u(t.closest), (uint32_t)t.best);
-            idx = atomicAdd(w.counts + 2, 1u);
-            have_ray = idx < count;
-            done = !have_ray;
-            if (have_ray) {
+        if (!done && t.node == EMPTY && pending == EMPTY) {
+            if (idx != 0xffffffffu) w.hit[idx] = make_uint2(f2u(t.closest), (uint32_t)t.best);
+            idx = atomicAdd(w.counts + 2, 1u);   // ptxas aggregates this per warp (REDUX + one ATOMG)
+            if (idx < count) {
                 const float4 o = __ldg(rays + 3 * (size_t)idx), d = __ldg(rays + 3 * (size_t)idx + 1);
                 cur.o = xyz(o); cur.d = xyz(d);
                 trav_begin<QN>(t, s, cur);
+                t.sp = 1;
+            } else {
+                done = true;
+                idx = 0xffffffffu;
             }
         }
         if (__all_sync(FULL, done)) break;
 
-        // ---- traverse until enough lanes want a refill
         for (;;) {
+            // ---- one inner-node visit for every lane that has one
             if (t.node >= 0) {
                 if (COUNT) st.nodes++;
-                trav_inner_step<QN>(t, s, stack);
+                trav_inner_step_lean<QN>(t, s, stack);
             }
-            if (t.node < 0 && t.node != VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY) {
+            // a lane that arrives at a leaf postpones it (once) and keeps traversing
+            bool at_leaf = (uint32_t)t.node > 0x80000000u;          // negative and not EMPTY
+            if (at_leaf && pending == EMPTY) {
                 pending = t.node;
-                t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
+                t.node = stack[--t.sp];
+                at_leaf = (uint32_t)t.node > 0x80000000u;
             }
             const bool inner = t.node >= 0;
-            const bool blocked = !inner && pending != VCRT_FAST_EMPTY;
             const unsigned mi = __ballot_sync(FULL, inner);
-            const unsigned mb = __ballot_sync(FULL, blocked);
-            if (mb != 0u && (__popc(mb) >= (int)a.leaf_threshold || mi == 0u)) {
-                if (pending != VCRT_FAST_EMPTY) {
+            const unsigned mb = __ballot_sync(FULL, !inner && pending != EMPTY);   // cannot go on without the leaf phase
+            const unsigned mf = __ballot_sync(FULL, !done && t.node == EMPTY && pending == EMPTY);
+            if (mb != 0u && (__popc(mb) >= leaf_t || mi == 0u)) {
+                // ---- leaf phase: every lane with a postponed leaf tests it
+                if (pending != EMPTY) {
                     if (COUNT) st.tris++;
                     trav_leaf_test(t, s, cur, pending);
-                    pending = VCRT_FAST_EMPTY;
-                    if (t.node < 0 && t.node != VCRT_FAST_EMPTY) {
+                    pending = EMPTY;
+                    if (at_leaf) {   // the leaf it was blocked on becomes the postponed one
                         pending = t.node;
-                        t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY;
+                        t.node = stack[--t.sp];
                     }
                 }
                 continue;
             }
-            const bool finished = !done && t.node == VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY;
-            const unsigned mf = __ballot_sync(FULL, finished);
-            if (mf != 0u && (__popc(mf) >= (int)a.shade_threshold || mi == 0u)) break;
-            if (mi == 0u && mb == 0u) break;
+            if (mf != 0u && (__popc(mf) >= refill_t || mi == 0u)) break;
+            if (mi == 0u) break;   // only done lanes left (mb == 0 and mf == 0 here)
         }
     }
     st.rays = 0u;
