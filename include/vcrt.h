@@ -95,6 +95,8 @@ typedef struct {
     uint64_t triangles;      /* triangle records fetched   (only with VCRT_FLAG_COUNT_TRAVERSAL) */
     double   kernel_ms;      /* device time of the render kernels (CUDA events) since the last reset */
     uint64_t launches;       /* kernels launched since the last reset */
+    double   trace_ms;       /* device time of the dominant kernel alone (wavefront trace launches; CUDA events per launch) */
+    uint64_t trace_launches; /* number of those launches */
 } vcrt_counters;
 
 enum { VCRT_OK = 0, VCRT_ERR_INVALID = -1, VCRT_ERR_CUDA = -2, VCRT_ERR_STATE = -3, VCRT_ERR_NOMEM = -4 };

@@ -52,6 +52,9 @@ struct vcrt_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     double kernel_ms = 0.0;
     uint64_t launches = 0;
+    TraceTimer trace_timer;
+    double trace_ms = 0.0;
+    uint64_t trace_launches = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -157,6 +160,7 @@ int vcrt_destroy(vcrt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    c->trace_timer.destroy();
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
     for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes}) if (b->ptr) cudaFree(b->ptr);
     if (c->d_counters) cudaFree(c->d_counters);
@@ -324,7 +328,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
         }
         nlaunch = 0;
         e = launch_render_wavefront(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream, (float4*)c->wf_q0.ptr, (float4*)c->wf_q1.ptr,
-                                    (uint2*)c->wf_hit.ptr, (float4*)c->wf_color.ptr, (unsigned int*)c->wf_counts.ptr, c->wf_capacity, &nlaunch);
+                                    (uint2*)c->wf_hit.ptr, (float4*)c->wf_color.ptr, (unsigned int*)c->wf_counts.ptr, c->wf_capacity, &nlaunch, &c->trace_timer);
     } else if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     else if (p.traversal == VCRT_TRAVERSAL_BRUTE_FORCE) e = launch_render_brute(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     else e = launch_render_reference(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
@@ -421,6 +425,7 @@ static int drain_events(vcrt_ctx* c) {
         cudaEventDestroy(ev.second);
     }
     c->events.clear();
+    c->trace_timer.drain(&c->trace_ms, &c->trace_launches);
     return VCRT_OK;
 }
 
@@ -434,6 +439,8 @@ int vcrt_get_counters(vcrt_ctx* c, vcrt_counters* out) {
     out->rays = h[0]; out->nodes = h[1]; out->triangles = h[2];
     out->kernel_ms = c->kernel_ms;
     out->launches = c->launches;
+    out->trace_ms = c->trace_ms;
+    out->trace_launches = c->trace_launches;
     return VCRT_OK;
 }
 
@@ -445,6 +452,8 @@ int vcrt_reset_counters(vcrt_ctx* c) {
     CU(c, cudaMemset(c->d_counters, 0, 3 * sizeof(unsigned long long)), "reset counters");
     c->kernel_ms = 0.0;
     c->launches = 0;
+    c->trace_ms = 0.0;
+    c->trace_launches = 0;
     return VCRT_OK;
 }
 

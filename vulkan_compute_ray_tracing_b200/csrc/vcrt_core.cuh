@@ -81,8 +81,29 @@ VCRT_HD Words8 ldg8(const Words8* p) {
 #endif
 }
 
+// Hint: bring the line holding p into L1 (no register, no scoreboard wait).  No-op on the host.
+VCRT_HD void prefetch_l1(const void* p) {
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // 15-bit fixed point -> float m = 0.5 * (1 + q / 32768) in [0.5, 1), exactly, in one PRMT: the 16-bit field becomes
 // bits 8..23 of a float whose exponent byte is 0x3F (bit 23 = the field's top bit = 0).
+// Same with the half chosen by a PRMT selector held in a register: 0x7104 = low half, 0x7324 = high half.  The
+// traversal keeps one selector per axis (by the sign of the ray direction) so that the near and far planes of a box come
+// out of the decode directly, without the min/max pair of the generic slab test.
+#define VCRT_Q15_SEL_LO 0x7104u
+#define VCRT_Q15_SEL_HI 0x7324u
+VCRT_HD float q15_sel(uint32_t w, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(w, 0x3F000000u, sel));
+#else
+    return u2f(0x3F000000u | ((sel == VCRT_Q15_SEL_LO ? (w & 0xffffu) : (w >> 16)) << 8));
+#endif
+}
 VCRT_HD float q15_lo(uint32_t w) {
 #ifdef __CUDA_ARCH__
     return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104));

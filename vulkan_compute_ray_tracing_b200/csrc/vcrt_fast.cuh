@@ -33,6 +33,7 @@ VCRT_HD float fmax_(float a, float b) { return fmaxf(a, b); }
 // interleave the rays of a warp; hit_bvh_fast below runs the same steps to completion for one ray.
 struct TravState {
     float3 idir, ood;       // 1/d (guarded) and o/d for the fma slab test; quantised nodes: 2*qext/d and (o - qorg)/d
+    uint32_t selx, sely, selz;   // quantised nodes: PRMT selector of the NEAR plane per axis (far = sel ^ 0x0220)
     float closest;
     int32_t best;           // winning triangle slot or -1
     int32_t node;           // >= 0 inner node to visit, < 0 leaf (~slot), VCRT_FAST_EMPTY: nothing left
@@ -49,6 +50,10 @@ VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
         // t(bound) = (qorg + 2m*qext - o) / d = m * (2*qext/d) - (o - qorg)/d
         t.ood = f3((r.o.x - s.qorg.x) * t.idir.x, (r.o.y - s.qorg.y) * t.idir.y, (r.o.z - s.qorg.z) * t.idir.z);
         t.idir = f3(2.0f * s.qext.x * t.idir.x, 2.0f * s.qext.y * t.idir.y, 2.0f * s.qext.z * t.idir.z);
+        // the plane entered first along an axis is the min plane when the ray travels in +axis, else the max plane
+        t.selx = t.idir.x >= 0.0f ? VCRT_Q15_SEL_LO : VCRT_Q15_SEL_HI;
+        t.sely = t.idir.y >= 0.0f ? VCRT_Q15_SEL_LO : VCRT_Q15_SEL_HI;
+        t.selz = t.idir.z >= 0.0f ? VCRT_Q15_SEL_LO : VCRT_Q15_SEL_HI;
     } else {
         t.ood = f3(r.o.x * t.idir.x, r.o.y * t.idir.y, r.o.z * t.idir.z);
     }
@@ -61,17 +66,27 @@ VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
 // Both children of inner node t.node against the ray: entry distances (clamped to 0), hit verdicts and child codes.
 template <int QN>
 VCRT_HD void trav_test_children(const TravState& t, const SceneView& s, float& lN, float& rN, bool& hl, bool& hr, int32_t& cl, int32_t& cr) {
-    float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
     if (QN) {
+        // near/far planes picked by the direction sign at decode time: no per-axis min/max
         const Words8 n = ldg8(s.qnodes + t.node);
-        lx0 = fmaf(q15_lo(n.w[0]), t.idir.x, -t.ood.x); lx1 = fmaf(q15_hi(n.w[0]), t.idir.x, -t.ood.x);
-        ly0 = fmaf(q15_lo(n.w[1]), t.idir.y, -t.ood.y); ly1 = fmaf(q15_hi(n.w[1]), t.idir.y, -t.ood.y);
-        lz0 = fmaf(q15_lo(n.w[2]), t.idir.z, -t.ood.z); lz1 = fmaf(q15_hi(n.w[2]), t.idir.z, -t.ood.z);
-        rx0 = fmaf(q15_lo(n.w[3]), t.idir.x, -t.ood.x); rx1 = fmaf(q15_hi(n.w[3]), t.idir.x, -t.ood.x);
-        ry0 = fmaf(q15_lo(n.w[4]), t.idir.y, -t.ood.y); ry1 = fmaf(q15_hi(n.w[4]), t.idir.y, -t.ood.y);
-        rz0 = fmaf(q15_lo(n.w[5]), t.idir.z, -t.ood.z); rz1 = fmaf(q15_hi(n.w[5]), t.idir.z, -t.ood.z);
+        const uint32_t fx = t.selx ^ 0x0220u, fy = t.sely ^ 0x0220u, fz = t.selz ^ 0x0220u;
+        const float lnx = fmaf(q15_sel(n.w[0], t.selx), t.idir.x, -t.ood.x), lfx = fmaf(q15_sel(n.w[0], fx), t.idir.x, -t.ood.x);
+        const float lny = fmaf(q15_sel(n.w[1], t.sely), t.idir.y, -t.ood.y), lfy = fmaf(q15_sel(n.w[1], fy), t.idir.y, -t.ood.y);
+        const float lnz = fmaf(q15_sel(n.w[2], t.selz), t.idir.z, -t.ood.z), lfz = fmaf(q15_sel(n.w[2], fz), t.idir.z, -t.ood.z);
+        const float rnx = fmaf(q15_sel(n.w[3], t.selx), t.idir.x, -t.ood.x), rfx = fmaf(q15_sel(n.w[3], fx), t.idir.x, -t.ood.x);
+        const float rny = fmaf(q15_sel(n.w[4], t.sely), t.idir.y, -t.ood.y), rfy = fmaf(q15_sel(n.w[4], fy), t.idir.y, -t.ood.y);
+        const float rnz = fmaf(q15_sel(n.w[5], t.selz), t.idir.z, -t.ood.z), rfz = fmaf(q15_sel(n.w[5], fz), t.idir.z, -t.ood.z);
         cl = (int32_t)n.w[6]; cr = (int32_t)n.w[7];
-    } else {
+        lN = fmax_(fmax_(lnx, lny), fmax_(lnz, 0.0f));
+        rN = fmax_(fmax_(rnx, rny), fmax_(rnz, 0.0f));
+        const float lF = fmin_(fmin_(lfx, lfy), lfz) * 1.0000004f;
+        const float rF = fmin_(fmin_(rfx, rfy), rfz) * 1.0000004f;
+        hl = lN <= fmin_(lF, t.closest);
+        hr = rN <= fmin_(rF, t.closest);
+        return;
+    }
+    float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
+    {
         const float4* p = s.fnodes + 4 * (size_t)t.node;
         const float4 n0 = ldg4(p), n1 = ldg4(p + 1), n2 = ldg4(p + 2), n3 = ldg4(p + 3);
         lx0 = fmaf(n0.x, t.idir.x, -t.ood.x); lx1 = fmaf(n0.y, t.idir.x, -t.ood.x);

@@ -101,20 +101,22 @@ __global__ void wf_reset_kernel(unsigned int* counts, int which) {
 }
 
 template <int SHADER, int RNG_MODE, int TRIG>
-static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
-    // the four trace variants: [COUNT][QN]
+static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
+    // the trace variants: [COUNT][QN][PRIMARY]
     typedef void (*TraceFn)(const KernelArgs, const WfQueues, const WfBatch);
-    static const TraceFn trace_fn[2][2] = {{wf_trace_kernel<false, 0>, wf_trace_kernel<false, 1>}, {wf_trace_kernel<true, 0>, wf_trace_kernel<true, 1>}};
-    static int trace_grid[2][2] = {{0, 0}, {0, 0}}, sms = 0;
+    static const TraceFn trace_fn[2][2][2] = {{{wf_trace_kernel<false, 0, false>, wf_trace_kernel<false, 0, true>}, {wf_trace_kernel<false, 1, false>, wf_trace_kernel<false, 1, true>}},
+                                              {{wf_trace_kernel<true, 0, false>, wf_trace_kernel<true, 0, true>}, {wf_trace_kernel<true, 1, false>, wf_trace_kernel<true, 1, true>}}};
+    static int trace_grid[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}}, sms = 0;
     if (sms == 0) {
         int dev = 0, per_sm = 0;
         cudaError_t e;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         for (int c = 0; c < 2; ++c)
-            for (int q = 0; q < 2; ++q) {
-                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_fn[c][q], VCRT_PBLOCK, 0)) != cudaSuccess) return e;
-                trace_grid[c][q] = sms * (per_sm > 0 ? per_sm : 1);
-            }
+            for (int q = 0; q < 2; ++q)
+                for (int p = 0; p < 2; ++p) {
+                    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_fn[c][q][p], VCRT_PBLOCK, 0)) != cudaSuccess) return e;
+                    trace_grid[c][q][p] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: one resident wave
+                }
     }
     const int ci = count ? 1 : 0, qi = a.scene.qnodes ? 1 : 0;
     const uint32_t items = a.owned_tiles * 1024u;
@@ -126,15 +128,17 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, 
         b.nitems = items - item0 < per_batch ? items - item0 : per_batch;
         b.npaths = b.nitems * a.sample_count;
         b.cur = 0u; b.bounce = 0u;
-        cudaError_t e = cudaMemsetAsync(w.counts, 0, 3 * sizeof(unsigned int), stream);
-        if (e != cudaSuccess) return e;
-        wf_generate_kernel<RNG_MODE><<<(b.npaths + 255u) / 256u, 256, 0, stream>>>(a, w, b);
-        ++*launches;
+        cudaError_t e;
         for (uint32_t bounce = 0; bounce < a.env.max_bounces; ++bounce) {
             b.bounce = bounce;
+            const int pi = bounce == 0u ? 1 : 0;   // bounce 0 reads no queue: rays are generated from the path id
             wf_reset_kernel<<<1, 1, 0, stream>>>(w.counts, (int)(b.cur ^ 1u));
-            trace_fn[ci][qi]<<<trace_grid[ci][qi], VCRT_PBLOCK, 0, stream>>>(a, w, b);
-            wf_shade_kernel<SHADER, RNG_MODE, TRIG><<<shade_grid, 256, 0, stream>>>(a, w, b);
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (timer && (e = timer->begin(stream, &t0, &t1)) != cudaSuccess) return e;
+            trace_fn[ci][qi][pi]<<<trace_grid[ci][qi][pi], VCRT_PBLOCK, 0, stream>>>(a, w, b);
+            if (timer && (e = timer->end(stream, t0, t1)) != cudaSuccess) return e;
+            if (pi) wf_shade_kernel<SHADER, RNG_MODE, TRIG, true><<<shade_grid, 256, 0, stream>>>(a, w, b);
+            else wf_shade_kernel<SHADER, RNG_MODE, TRIG, false><<<shade_grid, 256, 0, stream>>>(a, w, b);
             *launches += 3;
             b.cur ^= 1u;
         }
@@ -146,24 +150,25 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, 
 }
 
 template <int SHADER, int RNG_MODE>
-static cudaError_t wf_trig(const KernelArgs& a, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
-    if (trig == VCRT_TRIG_PORTABLE) return wf_run<SHADER, RNG_MODE, VCRT_TRIG_PORTABLE>(a, count, stream, w, launches);
-    return wf_run<SHADER, RNG_MODE, VCRT_TRIG_LIBM>(a, count, stream, w, launches);
+static cudaError_t wf_trig(const KernelArgs& a, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
+    if (trig == VCRT_TRIG_PORTABLE) return wf_run<SHADER, RNG_MODE, VCRT_TRIG_PORTABLE>(a, count, stream, w, launches, timer);
+    return wf_run<SHADER, RNG_MODE, VCRT_TRIG_LIBM>(a, count, stream, w, launches, timer);
 }
 
 template <int SHADER>
-static cudaError_t wf_rng(const KernelArgs& a, int rng, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches) {
-    if (rng == VCRT_RNG_PHILOX) return wf_trig<SHADER, VCRT_RNG_PHILOX>(a, trig, count, stream, w, launches);
-    return wf_trig<SHADER, VCRT_RNG_PCG_REF>(a, trig, count, stream, w, launches);
+static cudaError_t wf_rng(const KernelArgs& a, int rng, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
+    if (rng == VCRT_RNG_PHILOX) return wf_trig<SHADER, VCRT_RNG_PHILOX>(a, trig, count, stream, w, launches, timer);
+    return wf_trig<SHADER, VCRT_RNG_PCG_REF>(a, trig, count, stream, w, launches, timer);
 }
 
 cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream,
-                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches) {
+                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches,
+                                    TraceTimer* timer) {
     if (a.owned_tiles == 0u) return cudaSuccess;
     WfQueues w;
     w.q[0] = q0; w.q[1] = q1; w.hit = hit; w.sample_color = sample_color; w.counts = counts; w.capacity = capacity;
-    if (shader == VCRT_SHADER_SIMPLE) return wf_rng<VCRT_SHADER_SIMPLE>(a, rng, trig, count, stream, w, launches);
-    return wf_rng<VCRT_SHADER_FULL>(a, rng, trig, count, stream, w, launches);
+    if (shader == VCRT_SHADER_SIMPLE) return wf_rng<VCRT_SHADER_SIMPLE>(a, rng, trig, count, stream, w, launches, timer);
+    return wf_rng<VCRT_SHADER_FULL>(a, rng, trig, count, stream, w, launches, timer);
 }
 #endif
 

@@ -1,6 +1,8 @@
 // vcrt_launch.h -- host-visible launchers of the render kernels (one per traversal mode / translation unit).
 #pragma once
 #include <cuda_runtime.h>
+#include <utility>
+#include <vector>
 #include "vcrt_path.cuh"
 
 #define VCRT_BLOCK 128
@@ -8,14 +10,56 @@
 #define VCRT_PBLOCK 128   /* persistent kernel: threads per block */
 #endif
 #ifndef VCRT_PMINB
-#define VCRT_PMINB 1     /* persistent kernel: min resident blocks per SM (register cap) */
+#define VCRT_PMINB 10    /* persistent kernels: min resident blocks per SM = register cap 48 (r01 A/B on C3: 1 -> 4328, 9 -> 4487, 10 -> 4586, 12 -> 4516 Mrays/s) */
+#endif
+
+#ifndef VCRT_MEGA_MINB
+#define VCRT_MEGA_MINB 1  /* megakernel (A/B variant): it carries the shading state too, no register cap */
+#endif
+#ifndef VCRT_PREFETCH
+#define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
 #endif
 
 namespace vcrt {
 struct WfQueues;
+
+// CUDA events around every launch of the dominant kernel (wf_trace_kernel), recorded on the launching stream, so that the
+// roofline's kernel duration is measured live in the timed region.  Events are pooled: no creation cost in steady state.
+struct TraceTimer {
+    std::vector<cudaEvent_t> pool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    cudaError_t begin(cudaStream_t stream, cudaEvent_t* t0, cudaEvent_t* t1) {
+        cudaEvent_t* ev[2] = {t0, t1};
+        for (cudaEvent_t* e : ev) {
+            if (!pool.empty()) { *e = pool.back(); pool.pop_back(); continue; }
+            cudaError_t rc = cudaEventCreate(e);
+            if (rc != cudaSuccess) return rc;
+        }
+        return cudaEventRecord(*t0, stream);
+    }
+    cudaError_t end(cudaStream_t stream, cudaEvent_t t0, cudaEvent_t t1) {
+        pending.emplace_back(t0, t1);
+        return cudaEventRecord(t1, stream);
+    }
+    // after a stream synchronise: total milliseconds and count of the pending launches; events go back to the pool
+    void drain(double* ms, uint64_t* n) {
+        for (auto& p : pending) {
+            float f = 0.0f;
+            if (cudaEventElapsedTime(&f, p.first, p.second) == cudaSuccess) { *ms += f; ++*n; }
+            pool.push_back(p.first); pool.push_back(p.second);
+        }
+        pending.clear();
+    }
+    void destroy() {
+        for (auto& p : pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+        pending.clear(); pool.clear();
+    }
+};
 // Wavefront pipeline of the fast traversal (vcrt_wavefront.cuh); queues are owned by the context.
 cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream,
-                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches);
+                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches,
+                                    TraceTimer* timer);
 cudaError_t launch_render_reference(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_fast(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_brute(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);

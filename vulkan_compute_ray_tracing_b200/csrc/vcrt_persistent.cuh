@@ -21,7 +21,7 @@ namespace vcrt {
 
 
 template <int SHADER, int RNG_MODE, int TRIG, bool COUNT>
-__global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) render_persistent_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent_kernel(const __grid_constant__ KernelArgs a) {
     const unsigned FULL = 0xffffffffu;
     const uint32_t total_items = a.owned_tiles * 1024u;
     const bool f32 = a.accum_mode == VCRT_ACCUM_F32;
@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) render_persistent_ker
     float3 thr = f3(1, 1, 1);
     TravState t;
     t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = VCRT_FAST_EMPTY; t.sp = 0;
+    t.selx = t.sely = t.selz = VCRT_Q15_SEL_LO;
     int32_t pending = VCRT_FAST_EMPTY;
     int32_t stack[VCRT_FAST_STACK];
     bool have_ray = false;          // a ray is in flight (or just finished traversal and awaits shading)

@@ -1,5 +1,5 @@
-// vcrt_wavefront.cuh -- wavefront formulation of the fast path (GPU only): ray-gen, trace and shade are separate
-// kernels that hand dense ray queues to each other through HBM.
+// vcrt_wavefront.cuh -- wavefront formulation of the fast path (GPU only): trace and shade are separate kernels that
+// hand dense ray queues to each other through HBM; primary rays are never stored (bounce 0 derives them from the path id).
 //
 // Why: in the megakernel (vcrt_persistent.cuh) shading runs inside the traversal warps with a handful of lanes active
 // (ncu: ~30 % of issued instructions at 2-7 active lanes), and lanes that finished a ray idle until enough of them
@@ -45,40 +45,37 @@ __device__ __forceinline__ uint32_t wf_append_slot(unsigned int* counter, bool w
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
-// ---- ray generation: one thread per path of the batch (main(), ray-trace-compute.comp:352-373, :317-319)
-template <int RNG_MODE>
-__global__ void __launch_bounds__(256) wf_generate_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
-    const uint32_t path = blockIdx.x * 256u + threadIdx.x;
-    bool valid = false;
-    uint32_t x = 0, y = 0, k = 0;
-    if (path < b.npaths) {
-        const uint32_t it = path / a.sample_count;
-        k = path - it * a.sample_count;
-        valid = item_to_pixel(a, b.item0 + it, x, y);
-    }
-    const uint32_t slot = wf_append_slot(w.counts + 0, valid);
-    if (!valid) return;
+// Path id of a batch -> its pixel and sample (consecutive ids = the samples of one pixel).  False for pixels outside the
+// covered extent (ragged edge tiles).
+__device__ __forceinline__ bool wf_path_pixel(const KernelArgs& a, const WfBatch& b, uint32_t path, uint32_t& x, uint32_t& y, uint32_t& k) {
+    const uint32_t it = path / a.sample_count;
+    k = path - it * a.sample_count;
+    return item_to_pixel(a, b.item0 + it, x, y);
+}
+
+// The first ray of a path (main(), ray-trace-compute.comp:352-373, :317-319) and the PCG seed (random.glsl:19).  In
+// bounce 0 the trace and shade kernels compute it from the path id instead of reading it from a queue: a queue of
+// primary rays would cost 48 B written + 80 B read per path for values that are a few flops away.
+__device__ __forceinline__ void wf_primary(const KernelArgs& a, uint32_t x, uint32_t y, uint32_t k, Ray& r, uint32_t& rng) {
     const Ray pr = primary_ray(a.cam, x, y);
-    const float3 d = normalize(pr.d);
-    const uint32_t rng = (600u * x + y) * (a.sample_begin + k + 1u);   // random.glsl:19 (PCG only)
-    float4* q = w.q[0] + 3 * (size_t)slot;
-    q[0] = make_float4(pr.o.x, pr.o.y, pr.o.z, u2f(path));
-    q[1] = make_float4(d.x, d.y, d.z, u2f(rng));
-    q[2] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    r.o = pr.o;
+    r.d = normalize(pr.d);
+    rng = (600u * x + y) * (a.sample_begin + k + 1u);
 }
 
 // ---- trace: persistent warps, lanes refill from the queue; result = {t, slot} per ray
 // Lane state: t.node (inner node >= 0 | leaf code < 0 | EMPTY), one postponed leaf, the stack with its sentinel.  The
 // loop body is written for predication (trav_inner_step_lean): ncu on the branchy version showed ~50 of ~110 warp
 // instructions per iteration spent on control flow around the 57-instruction box test (profiles/r01_v4_*).
-template <bool COUNT, int QN>
+// PRIMARY (bounce 0): the "queue" is implicit -- ray i is the primary ray of path i of the batch.
+template <bool COUNT, int QN, bool PRIMARY>
 __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
     const unsigned FULL = 0xffffffffu;
     const int32_t EMPTY = VCRT_FAST_EMPTY;
     const SceneView& s = a.scene;
-    const uint32_t count = w.counts[b.cur];
+    const uint32_t count = PRIMARY ? b.npaths : w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(a.counters + 0, (unsigned long long)count);
+    if (!PRIMARY && blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(a.counters + 0, (unsigned long long)count);
     const int leaf_t = (int)a.leaf_threshold, refill_t = (int)a.shade_threshold;
 
     uint32_t idx = 0xffffffffu;          // ray in flight (0xffffffff: none)
@@ -86,6 +83,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
     Ray cur; cur.o = cur.d = f3(0, 0, 0);
     TravState t;
     t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = EMPTY; t.sp = 0;
+    t.selx = t.sely = t.selz = VCRT_Q15_SEL_LO;
     int32_t pending = EMPTY;
     int32_t stack[VCRT_FAST_STACK];
     stack[0] = EMPTY;                    // sentinel: popping an exhausted stack yields EMPTY
@@ -97,10 +95,19 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             if (idx != 0xffffffffu) w.hit[idx] = make_uint2(f2u(t.closest), (uint32_t)t.best);
             idx = atomicAdd(w.counts + 2, 1u);   // ptxas aggregates this per warp (REDUX + one ATOMG)
             if (idx < count) {
-                const float4 o = __ldg(rays + 3 * (size_t)idx), d = __ldg(rays + 3 * (size_t)idx + 1);
-                cur.o = xyz(o); cur.d = xyz(d);
+                bool valid = true;
+                if (PRIMARY) {
+                    uint32_t x, y, k, rng;
+                    valid = wf_path_pixel(a, b, idx, x, y, k);
+                    wf_primary(a, x, y, k, cur, rng);
+                    if (valid) st.rays++;
+                } else {
+                    const float4 o = __ldg(rays + 3 * (size_t)idx), d = __ldg(rays + 3 * (size_t)idx + 1);
+                    cur.o = xyz(o); cur.d = xyz(d);
+                }
                 trav_begin<QN>(t, s, cur);
                 t.sp = 1;
+                if (!valid) { t.node = EMPTY; idx = 0xffffffffu; }   // a path outside the covered extent: nothing to trace or record
             } else {
                 done = true;
                 idx = 0xffffffffu;
@@ -118,6 +125,13 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             bool at_leaf = (uint32_t)t.node > 0x80000000u;          // negative and not EMPTY
             if (at_leaf && pending == EMPTY) {
                 pending = t.node;
+#if VCRT_PREFETCH >= 1
+                {   // the triangle is tested some iterations from now: start pulling its record (48 B, may straddle two lines) into L1
+                    const char* tp = (const char*)(s.ftris + 3 * (size_t)(~pending));
+                    prefetch_l1(tp);
+                    prefetch_l1(tp + 47);
+                }
+#endif
                 t.node = stack[--t.sp];
                 at_leaf = (uint32_t)t.node > 0x80000000u;
             }
@@ -133,6 +147,11 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                     pending = EMPTY;
                     if (at_leaf) {   // the leaf it was blocked on becomes the postponed one
                         pending = t.node;
+#if VCRT_PREFETCH >= 1
+                        const char* tp = (const char*)(s.ftris + 3 * (size_t)(~pending));
+                        prefetch_l1(tp);
+                        prefetch_l1(tp + 47);
+#endif
                         t.node = stack[--t.sp];
                     }
                 }
@@ -142,34 +161,43 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             if (mi == 0u) break;   // only done lanes left (mb == 0 and mf == 0 here)
         }
     }
-    st.rays = 0u;
-    flush_stats(a, st);
+    flush_stats(a, st);   // st.rays is non-zero only for PRIMARY (queued rays are counted once per launch above)
 }
 
 // ---- shade: one thread per traced ray (ray_color body, ray-trace-compute.comp:321-340)
-template <int SHADER, int RNG_MODE, int TRIG>
+template <int SHADER, int RNG_MODE, int TRIG, bool PRIMARY>
 __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
     const SceneView& s = a.scene;
-    const uint32_t count = w.counts[b.cur];
+    const uint32_t count = PRIMARY ? b.npaths : w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
     float4* __restrict__ next = w.q[b.cur ^ 1u];
     for (uint32_t base = blockIdx.x * 256u; base < count; base += gridDim.x * 256u) {   // base is warp-uniform
         const uint32_t i = base + threadIdx.x;
         bool cont = false;
         float4 q0, q1, q2;
-        if (i < count) {
-            q0 = rays[3 * (size_t)i]; q1 = rays[3 * (size_t)i + 1]; q2 = rays[3 * (size_t)i + 2];
+        uint32_t x = 0, y = 0, k = 0;
+        const bool live = i < count && (!PRIMARY || wf_path_pixel(a, b, i, x, y, k));
+        if (live) {
+            Ray cur;
+            float3 thr;
+            uint32_t path, rng;
+            if (PRIMARY) {
+                path = i;
+                wf_primary(a, x, y, k, cur, rng);
+                thr = f3(1.0f, 1.0f, 1.0f);
+                q0 = make_float4(0, 0, 0, u2f(path));
+            } else {
+                q0 = rays[3 * (size_t)i]; q1 = rays[3 * (size_t)i + 1]; q2 = rays[3 * (size_t)i + 2];
+                path = f2u(q0.w); rng = f2u(q1.w);
+                cur.o = xyz(q0); cur.d = xyz(q1);
+                thr = xyz(q2);
+                wf_path_pixel(a, b, path, x, y, k);
+            }
             const uint2 h = w.hit[i];
-            const uint32_t path = f2u(q0.w);
-            Ray cur; cur.o = xyz(q0); cur.d = xyz(q1);
-            float3 thr = xyz(q2);
             TravState t;
             t.closest = u2f(h.x); t.best = (int32_t)h.y;
             Hit rec;
             const bool hit = trav_finish(t, s, cur, rec);
-            const uint32_t it = path / a.sample_count, k = path - it * a.sample_count;
-            uint32_t x, y;
-            item_to_pixel(a, b.item0 + it, x, y);
             const uint32_t pix = y * a.W + x;
             if (b.bounce == 0 && k == 0 && (a.flags & VCRT_FLAG_WRITE_AOV)) {
                 vcrt_aov o;
@@ -179,7 +207,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ K
             }
             if (hit) {
                 Rng g;
-                g.pcg = f2u(q1.w);
+                g.pcg = rng;
                 g.key0 = pix; g.key1 = a.philox_seed; g.ctr0 = a.sample_begin + k;
                 rng_begin_bounce<RNG_MODE>(g, b.bounce);
                 float3 albedo;
