@@ -13,8 +13,11 @@ region.
   e2e       the same metric through the public API with HOST buffers: every step uploads the five scene buffers from
             pinned host memory (incl. the repack for the fast traversal), renders, resolves and reads the rgba8 target
             back; wall clock between synchronised barriers, max over ranks.
-  roofline  HBM-bound traversal roofline: algorithmic bytes per ray B_ray = 48*(nodes + triangles) of the canonical
-            (reference-order, t-culled) traversal, counted by the CPU oracle on a tile sample of the same ray set.
+  roofline  HBM-bound traversal roofline for the dominant kernel (wf_trace_kernel, timed per launch with CUDA events on
+            its stream inside the timed region): algorithmic bytes per ray B_ray = 48*(nodes + triangles) of the canonical
+            (reference-order, t-culled) traversal, counted by the CPU oracle on a tile sample of the same ray set
+            (SURVEY.md 8d).  The kernel walks a SAH tree rebuilt over the same leaves and fetches far fewer bytes, so
+            `frac` exceeds 1; `own_*` gives the bytes the kernel actually requests (its own node/triangle counters).
   cpu_baseline / --impl reference
             the reference's own shader text compiled for the CPU (oracle/_ref, kind "reference"; falls back to the
             restated oracle, kind "port") on all host cores, on a bounded sample of the same workload.
@@ -226,9 +229,13 @@ def main():
     torch.cuda.set_stream(stream)
     mat.setStream(stream.cuda_stream)
 
-    params = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
-                                stack_depth=64, sample_begin=rank * args.spp, sample_count=args.spp, philox_seed=args.scene_seed,
-                                flags=vcrt.FLAG_STATIC_KERNEL if args.static_kernel else 0)
+    from vulkan_compute_ray_tracing_b200 import sharding
+    base = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
+                              stack_depth=64, sample_begin=0, sample_count=args.spp * world, philox_seed=args.scene_seed,
+                              flags=vcrt.FLAG_STATIC_KERNEL if args.static_kernel else 0)
+    # weak scaling: the job is an (spp x world)-sample frame, rank r renders its contiguous slice of args.spp samples
+    params, _ = sharding.shard_params(base, "samples", rank, world)
+    assert params.sample_count == args.spp and params.sample_begin == rank * args.spp
     ptr, nbytes = mat.devicePtr(2)
 
     class _Wrap:
@@ -273,6 +280,7 @@ def main():
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     c = mat.counters()
     rays, kernel_ms, launches = int(c.rays), float(c.kernel_ms), int(c.launches)
+    trace_ms, trace_launches = float(c.trace_ms), int(c.trace_launches)
     tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device="cuda")
     mx = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -315,14 +323,48 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.SUM)
             dist.all_reduce(m2, op=dist.ReduceOp.MAX)
         e2e = {"value": float(t2[0]) / float(m2[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes),
-               "ms_per_step": 1e3 * float(m2[0]) / args.steps}
+               "ms_per_step": 1e3 * float(m2[0]) / args.steps,
+               "includes": "upload of the 5 scene buffers from pinned host memory + host rebuild of the traversal records + render + resolve + rgba8 read-back"}
+
+        # the reference's own per-frame protocol (main.cpp:166-183, :228): scene resident, 32-byte UBO in, frame out
+        def frame_step():
+            ubo.buffers[0].write(vcrt.pack_ubo(CAM, 0, scene))
+            step()
+            if rank == 0:
+                mat._check(L.vcrt_read_target_rgba8(mat._ctx, out_host.ctypes.data, out_host.nbytes))
+            else:
+                mat.synchronize()
+
+        frame_step()
+        barrier()
+        mat.resetCounters()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        c3 = mat.counters()
+        t3 = torch.tensor([float(c3.rays)], dtype=torch.float64, device="cuda")
+        m3 = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.SUM)
+            dist.all_reduce(m3, op=dist.ReduceOp.MAX)
+        e2e["scene_resident"] = {"value": float(t3[0]) / float(m3[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 32,
+                                 "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": 1e3 * float(m3[0]) / args.steps}
 
     if rank == 0:
         peak, peak_src = measured_peak()
         subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
         bray, bray_info = oracle_bray(scene, w, h, args.bounces, tile_count=32)
-        rays_per_launch = rays / max(args.steps, 1)
-        kernel_s = kernel_ms * 1e-3 / max(args.steps, 1)      # the render kernel's average launch duration (CUDA events on its stream)
+        # dominant kernel = wf_trace_kernel: every ray passes through exactly one of its launches
+        if trace_launches:
+            rays_per_launch = rays / trace_launches
+            kernel_s = trace_ms * 1e-3 / trace_launches   # average launch duration, CUDA events on the launching stream, timed region
+            kname = "wf_trace_kernel"
+        else:                                              # A/B variants without a separate trace kernel: the whole render
+            rays_per_launch = rays / max(args.steps, 1)
+            kernel_s = kernel_ms * 1e-3 / max(args.steps, 1)
+            kname = "render kernel"
         achieved = bray * rays_per_launch / kernel_s / 1e9
         traffic = None
         try:
@@ -330,12 +372,25 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
+        # what the kernel itself requests: its node/triangle counters on one 1-spp pass (untimed, counting build of the kernel)
+        cp = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
+                                stack_depth=64, sample_begin=0, sample_count=1, philox_seed=args.scene_seed, flags=vcrt.FLAG_COUNT_TRAVERSAL)
+        mat.clearAccum(); mat.resetCounters()
+        model.renderCommand(None, 0, cp)
+        cc = mat.counters()
+        node_bytes = 32 if mat.getInfo("fast_nodes") == "q15" else 64
+        own_bray = (node_bytes * cc.nodes + 48 * cc.triangles) / max(cc.rays, 1)
+        own = {"own_bytes_per_ray": own_bray, "own_nodes_per_ray": cc.nodes / max(cc.rays, 1), "own_tris_per_ray": cc.triangles / max(cc.rays, 1),
+               "own_node_bytes": node_bytes, "own_achieved": own_bray * rays_per_launch / kernel_s / 1e9,
+               "own_frac": own_bray * rays_per_launch / kernel_s / 1e9 / peak}
         line = {"metric": "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, scene), "clocks": clocks, "gpu_launches": total_launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "peak_source": peak_src, "bytes_per_ray": bray, "roofline_mrays": peak * 1e3 / bray,
-                             "kernel_ms_per_launch": kernel_s * 1e3, "rays_per_launch": rays_per_launch, "canonical_traversal": bray_info},
+                             "peak_source": peak_src, "kernel": kname, "bytes_per_ray": bray, "roofline_mrays": peak * 1e3 / bray,
+                             "kernel_ms_per_launch": kernel_s * 1e3, "rays_per_launch": rays_per_launch, "launches_per_step": trace_launches / max(args.steps, 1),
+                             "kernel_share_of_step": (trace_ms / max(args.steps, 1)) / (max_ms / args.steps) if trace_launches else 1.0,
+                             "kernel_mrays": rays_per_launch / kernel_s / 1e6, "canonical_traversal": bray_info, **own},
                 "rays_per_step": total_rays / args.steps, "scene_build_s": gen_s}
         if e2e:
             line["e2e"] = e2e

@@ -150,8 +150,14 @@ int vcrt_write_accum_f32(vcrt_ctx* ctx, const void* src, size_t bytes); /* resum
 int vcrt_device_ptr(vcrt_ctx* ctx, int what /* 0 target rgba8, 1 accum rgba8, 2 accum f32, 3 aov */, void** out, size_t* bytes);
 
 /* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
- * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology). */
+ * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
+ * (default: 32-byte quantised nodes when the scene extent allows, else 64-byte float nodes), "q15", "f32"; "wf_batch_paths":
+ * paths per wavefront batch (queue memory: 120 B per path); "leaf_threshold" / "shade_threshold": lanes (1..32). */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
+
+/* Read-only facts about ctx as text: "fast_nodes" -> "q15" | "f32" | "none" (what the fast traversal walks after the last
+ * upload), "fast_node_count", "fast_depth", "wf_batch_paths", "device".  Builds the fast records if they are stale. */
+int vcrt_get_info(vcrt_ctx* ctx, const char* key, char* value, size_t capacity);
 
 /* Run ctx's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores ctx's own stream), so
  * that renders order with the caller's collectives / events without extra synchronisation.  Synchronises first. */

@@ -233,6 +233,13 @@ class ComputeMaterial:
         self._require()
         self._check(N.lib().vcrt_set_option(self._ctx, key.encode(), value.encode()))
 
+    def getInfo(self, key):
+        """Read-only facts as text, e.g. getInfo("fast_nodes") -> "q15" | "f32" | "none"."""
+        self._require()
+        buf = C.create_string_buffer(64)
+        self._check(N.lib().vcrt_get_info(self._ctx, key.encode(), buf, 64))
+        return buf.value.decode()
+
     def setStream(self, cuda_stream):
         """Run on a caller-owned CUDA stream (integer cudaStream_t handle, e.g. torch.cuda.current_stream().cuda_stream)."""
         self._require()

@@ -37,6 +37,7 @@ struct vcrt_ctx {
     bool quantized = false;
     float qorg[3] = {0, 0, 0}, qext[3] = {0, 0, 0};
     DevBuf qnodes;
+    uint32_t fast_depth = 0;
     bool fast_ok = false;
     std::string fast_err;
     DevBuf fnodes, ftris;
@@ -145,6 +146,26 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         return VCRT_OK;
     }
     return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: unknown option '" + k + "'");
+}
+
+static int prepare_fast(vcrt_ctx* c);
+
+int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
+    if (!c || !key || !value || capacity == 0) return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: NULL argument");
+    const std::string k(key);
+    std::string v;
+    if (k == "fast_nodes" || k == "fast_node_count" || k == "fast_depth") {
+        CU(c, cudaSetDevice(c->device), "set device");
+        const bool ok = prepare_fast(c) == VCRT_OK;
+        if (k == "fast_nodes") v = !ok ? "none" : c->quantized ? "q15" : "f32";
+        else if (k == "fast_node_count") v = std::to_string(ok ? c->nfnodes : 0u);
+        else v = std::to_string(ok ? c->fast_depth : 0u);
+    } else if (k == "wf_batch_paths") v = std::to_string(c->wf_batch);
+    else if (k == "device") v = std::to_string(c->device);
+    else return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: unknown key '" + k + "'");
+    if (v.size() + 1 > capacity) return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: buffer too small");
+    std::memcpy(value, v.c_str(), v.size() + 1);
+    return VCRT_OK;
 }
 
 int vcrt_set_stream(vcrt_ctx* c, void* cuda_stream) {
@@ -262,6 +283,7 @@ static int prepare_fast(vcrt_ctx* c) {
             CU(c, cudaStreamSynchronize(c->stream), "synchronize");
             c->froot = fb.root;
             c->nfnodes = fb.num_nodes();
+            c->fast_depth = fb.depth;
         }
     }
     if (!c->fast_ok) return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err);
