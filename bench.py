@@ -159,18 +159,29 @@ def run_reference_arm(args, rank):
     cores = os.cpu_count()
     sample = "%d x 1-spp frames of the %dx%d image per step (of %d spp), reference traversal, pcg_ref RNG" % (frames, args.width, args.height, args.spp)
     line = {"impl": "reference", "metric": "Mrays/s (primary+bounce)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
+# BASELINE.json configs[2..4].  c3 is the headline (weak scaling: 64 spp per GPU); c4 and c5 are fixed-size jobs (strong scaling).
+CONFIGS = {
+    "c3": dict(triangles=1000000, width=1920, height=1080, spp=64, sharding="samples", scaling="weak"),
+    "c4": dict(triangles=10000000, width=3840, height=2160, spp=16, sharding="tiles", scaling="strong"),
+    "c5": dict(triangles=1000000, width=3840, height=2160, spp=1024, sharding="samples", scaling="strong"),
+}
+
+
 def workload_config(args, scene):
-    return {"workload": "C3: synthetic %d-triangle lit box (seed %d), %dx%d, %d spp/GPU, depth %d, full shader, philox, f32 accum, fast traversal"
-                        % (len(scene["triangles"]) // 48, args.scene_seed, args.width, args.height, args.spp, args.bounces),
+    spp_txt = "%d spp/GPU" % args.spp if args.scaling == "weak" else "%d spp in total" % args.spp
+    shard = {"samples": "sample slices + NCCL reduce of the f32 accumulation buffers", "tiles": "32x32 tile interleave + NCCL all-gather of packed rgba8 tiles"}[args.sharding]
+    return {"workload": "%s: synthetic %d-triangle lit box (seed %d), %dx%d, %s, depth %d, full shader, philox, f32 accum, fast traversal"
+                        % (args.config.upper(), len(scene["triangles"]) // 48, args.scene_seed, args.width, args.height, spp_txt, args.bounces),
             "triangles": len(scene["triangles"]) // 48, "bvh_nodes": len(scene["bvh"]) // 48, "width": args.width, "height": args.height,
-            "spp_per_gpu": args.spp, "max_bounces": args.bounces, "sharding": "sample slices + NCCL reduce (weak)" if args.gpus > 1 else "none",
+            "spp": args.spp, "spp_is": "per GPU" if args.scaling == "weak" else "total", "max_bounces": args.bounces,
+            "sharding": (shard + " (%s)" % args.scaling) if args.gpus > 1 else "none",
             "l2": "flushed between timed steps (256 MiB memset)"}
 
 
@@ -180,11 +191,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--triangles", type=int, default=1000000)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json workload: c3 (headline), c4, c5")
+    ap.add_argument("--triangles", type=int, default=None)
     ap.add_argument("--scene-seed", type=int, default=1234)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--spp", type=int, default=None)
+    ap.add_argument("--sharding", default=None, choices=["samples", "tiles"])
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--traversal", default="fast")
     ap.add_argument("--ref-frames", type=int, default=1, help="1-spp frames per step of the CPU reference arm")
@@ -193,10 +206,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    for k, v in CONFIGS[args.config].items():
+        if getattr(args, k, None) is None:
+            setattr(args, k, v)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # host-side scene generation / record builds use OpenMP; torchrun exports OMP_NUM_THREADS=1, which would serialise them
+    host_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+    if args.impl == "ours":
+        os.environ["OMP_NUM_THREADS"] = str(host_threads)
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
@@ -225,17 +245,18 @@ def main():
     for name in order:
         mat.addStorageBufferBundle(vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), scene[name]))
     model = vcrt.ComputeModel(mat)
+    mat.setOption("host_threads", str(host_threads))
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by the kernels, NCCL and the timing events
     torch.cuda.set_stream(stream)
     mat.setStream(stream.cuda_stream)
 
     from vulkan_compute_ray_tracing_b200 import sharding
+    # weak scaling: the job is an (spp x world)-sample frame; strong scaling: an spp-sample frame whatever the world size
+    total_spp = args.spp * world if args.scaling == "weak" else args.spp
     base = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
-                              stack_depth=64, sample_begin=0, sample_count=args.spp * world, philox_seed=args.scene_seed,
+                              stack_depth=64, sample_begin=0, sample_count=total_spp, philox_seed=args.scene_seed,
                               flags=vcrt.FLAG_STATIC_KERNEL if args.static_kernel else 0)
-    # weak scaling: the job is an (spp x world)-sample frame, rank r renders its contiguous slice of args.spp samples
-    params, _ = sharding.shard_params(base, "samples", rank, world)
-    assert params.sample_count == args.spp and params.sample_begin == rank * args.spp
+    params, active = sharding.shard_params(base, args.sharding, rank, world)
     ptr, nbytes = mat.devicePtr(2)
 
     class _Wrap:
@@ -245,11 +266,16 @@ def main():
 
     def step():
         mat.clearAccum()
-        model.renderCommand(None, 0, params)
-        if world > 1:
-            dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            mat.resolve(args.spp * world, 0.0)
+        if active:
+            model.renderCommand(None, 0, params)
+        if args.sharding == "samples":
+            if world > 1:
+                sharding.reduce_accumulation(accum_t, dst=0)      # NCCL SUM reduce on the render stream
+            if rank == 0:
+                mat.resolve(total_spp, 0.0)
+        else:
+            mat.resolve(total_spp, 0.0)                           # every rank resolves its own tiles ...
+            sharding.gather_tiles_device(mat, 0, rank, world)     # ... and the packed rgba8 tiles are all-gathered
 
     def barrier():
         torch.cuda.synchronize()
@@ -290,17 +316,22 @@ def main():
     max_ms = float(mx[0])
     value = total_rays / (max_ms * 1e-3) / 1e6
 
-    # ---- e2e: host buffers in, rgba8 frame out, every step
+    # ---- e2e: through the public API with host buffers, host<->device copies inside the timed region.
+    # Headline protocol = the reference's own frame loop (main.cpp:166-183, :228, :323-395), which is also what the reference
+    # arm times: scene prepared once outside the timed region; per step the 32-byte UBO goes host -> device, the frame is
+    # rendered and resolved, and the rgba8 target comes back into pinned host memory.  `with_scene_upload` additionally
+    # re-uploads the five scene buffers from pinned host memory and rebuilds the traversal records on the host every step.
     e2e = None
     if not args.no_e2e:
         out_host = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
         L = __import__("vulkan_compute_ray_tracing_b200._native", fromlist=["lib"]).lib()
         h2d = sum(v[0].nbytes for v in pinned.values()) + 32
 
-        def e2e_step():
-            for i, name in enumerate(order):
-                a = pinned[name][0]
-                mat._check(L.vcrt_set_buffer(mat._ctx, 3 + i, a.ctypes.data if a.nbytes else None, a.nbytes))
+        def frame_step(upload):
+            if upload:
+                for i, name in enumerate(order):
+                    a = pinned[name][0]
+                    mat._check(L.vcrt_set_buffer(mat._ctx, 3 + i, a.ctypes.data if a.nbytes else None, a.nbytes))
             ubo.buffers[0].write(vcrt.pack_ubo(CAM, 0, scene))
             step()
             if rank == 0:
@@ -308,49 +339,29 @@ def main():
             else:
                 mat.synchronize()
 
-        e2e_step()
-        barrier()
-        mat.resetCounters()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        c2 = mat.counters()
-        t2 = torch.tensor([float(c2.rays)], dtype=torch.float64, device="cuda")
-        m2 = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
-            dist.all_reduce(m2, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(t2[0]) / float(m2[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes),
-               "ms_per_step": 1e3 * float(m2[0]) / args.steps,
-               "includes": "upload of the 5 scene buffers from pinned host memory + host rebuild of the traversal records + render + resolve + rgba8 read-back"}
+        def timed(upload, steps):
+            frame_step(upload)
+            barrier()
+            mat.resetCounters()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                frame_step(upload)
+            barrier()
+            dt = time.perf_counter() - t0
+            cc = mat.counters()
+            tr = torch.tensor([float(cc.rays)], dtype=torch.float64, device="cuda")
+            tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tr[0]) / float(tm[0]) / 1e6, 1e3 * float(tm[0]) / steps
 
-        # the reference's own per-frame protocol (main.cpp:166-183, :228): scene resident, 32-byte UBO in, frame out
-        def frame_step():
-            ubo.buffers[0].write(vcrt.pack_ubo(CAM, 0, scene))
-            step()
-            if rank == 0:
-                mat._check(L.vcrt_read_target_rgba8(mat._ctx, out_host.ctypes.data, out_host.nbytes))
-            else:
-                mat.synchronize()
-
-        frame_step()
-        barrier()
-        mat.resetCounters()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            frame_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        c3 = mat.counters()
-        t3 = torch.tensor([float(c3.rays)], dtype=torch.float64, device="cuda")
-        m3 = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t3, op=dist.ReduceOp.SUM)
-            dist.all_reduce(m3, op=dist.ReduceOp.MAX)
-        e2e["scene_resident"] = {"value": float(t3[0]) / float(m3[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 32,
-                                 "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": 1e3 * float(m3[0]) / args.steps}
+        v, ms = timed(False, args.steps)
+        e2e = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
+               "protocol": "reference frame loop: UBO write + computeCommand-equivalent render + resolve + rgba8 read-back to pinned host memory; scene resident"}
+        v, ms = timed(True, min(args.steps, 3))
+        e2e["with_scene_upload"] = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
+                                    "includes": "upload of the 5 scene buffers from pinned host memory + host rebuild of the traversal records, every step"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -384,7 +395,7 @@ def main():
                "own_node_bytes": node_bytes, "own_achieved": own_bray * rays_per_launch / kernel_s / 1e9,
                "own_frac": own_bray * rays_per_launch / kernel_s / 1e9 / peak}
         line = {"metric": "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, scene), "clocks": clocks, "gpu_launches": total_launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_src, "kernel": kname, "bytes_per_ray": bray, "roofline_mrays": peak * 1e3 / bray,
@@ -394,7 +405,7 @@ def main():
                 "rays_per_step": total_rays / args.steps, "scene_build_s": gen_s}
         if e2e:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == "c3":
             dt1, rays1, kind = cpu_reference_step(scene, w, h, args.bounces, 1)
             frames = int(min(max(round(15.0 / max(dt1, 1e-3)), 1), 16))
             dt, r, kind = cpu_reference_step(scene, w, h, args.bounces, frames, first_sample=1)

@@ -149,10 +149,18 @@ int vcrt_write_accum_f32(vcrt_ctx* ctx, const void* src, size_t bytes); /* resum
 /* Device pointers of ctx-owned images, for collectives (NCCL) and zero-copy consumers. */
 int vcrt_device_ptr(vcrt_ctx* ctx, int what /* 0 target rgba8, 1 accum rgba8, 2 accum f32, 3 aov */, void** out, size_t* bytes);
 
+/* Multi-GPU tile sharding (no reference counterpart: one VkDevice, VulkanApplicationContext.cpp:95-119).  Copies the
+ * pixels of the 32x32 tiles k with k % tile_count == tile_rank (row-major tile order, the partition of
+ * vcrt_render_params.tile_rank/tile_count) between a ctx image (what: 0 target rgba8, 2 f32 accumulation) and a packed
+ * DEVICE buffer: owned tiles back to back, 1024 pixels each, row-major inside the tile, zero outside the image.
+ * bytes >= owned_tiles * 1024 * (4 | 16).  Asynchronous on ctx's stream; pair with an all-gather of the packed buffers. */
+int vcrt_pack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile_count, void* packed_dev, size_t bytes);
+int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile_count, const void* packed_dev, size_t bytes);
+
 /* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
  * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
  * (default: 32-byte quantised nodes when the scene extent allows, else 64-byte float nodes), "q15", "f32"; "wf_batch_paths":
- * paths per wavefront batch (queue memory: 120 B per path); "leaf_threshold" / "shade_threshold": lanes (1..32). */
+ * paths per wavefront batch (queue memory: 120 B per path); "leaf_threshold" / "shade_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 
 /* Read-only facts about ctx as text: "fast_nodes" -> "q15" | "f32" | "none" (what the fast traversal walks after the last

@@ -55,6 +55,8 @@ SIGNATURES = {
     "vcrt_write_accum_f32": (C.c_int, [_P, _P, C.c_size_t]),
     "vcrt_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "vcrt_set_option": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
+    "vcrt_pack_tiles": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, _P, C.c_size_t]),
+    "vcrt_unpack_tiles": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, _P, C.c_size_t]),
     "vcrt_get_info": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_size_t]),
     "vcrt_set_stream": (C.c_int, [_P, _P]),
     "vcrt_synchronize": (C.c_int, [_P]),

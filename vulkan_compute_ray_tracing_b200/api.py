@@ -233,6 +233,15 @@ class ComputeMaterial:
         self._require()
         self._check(N.lib().vcrt_set_option(self._ctx, key.encode(), value.encode()))
 
+    def packTiles(self, what, tile_rank, tile_count, packed_ptr, nbytes):
+        """Owned tiles of image `what` (0 target rgba8, 2 f32 accumulation) -> packed device buffer (vcrt_pack_tiles)."""
+        self._require()
+        self._check(N.lib().vcrt_pack_tiles(self._ctx, what, tile_rank, tile_count, C.c_void_p(packed_ptr), nbytes))
+
+    def unpackTiles(self, what, tile_rank, tile_count, packed_ptr, nbytes):
+        self._require()
+        self._check(N.lib().vcrt_unpack_tiles(self._ctx, what, tile_rank, tile_count, C.c_void_p(packed_ptr), nbytes))
+
     def getInfo(self, key):
         """Read-only facts as text, e.g. getInfo("fast_nodes") -> "q15" | "f32" | "none"."""
         self._require()

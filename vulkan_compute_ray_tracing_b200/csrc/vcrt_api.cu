@@ -133,6 +133,12 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         if (m != c->fast_nodes) { c->fast_nodes = m; c->fast_dirty = true; }
         return VCRT_OK;
     }
+    if (k == "host_threads") {   // OpenMP threads of the host-side record build (launchers such as torchrun export OMP_NUM_THREADS=1)
+        const int n = atoi(value);
+        if (n < 1 || n > 1024) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: host_threads must be 1..1024");
+        set_repack_threads(n);
+        return VCRT_OK;
+    }
     if (k == "wf_batch_paths") {
         const long long n = atoll(value);
         if (n < 1024 || n > (1ll << 30)) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: wf_batch_paths must be 1024..2^30");
@@ -394,6 +400,29 @@ int vcrt_resolve(vcrt_ctx* c, uint32_t total_samples, float gamma) {
        "launch resolve kernel");
     c->launches += 1;
     return VCRT_OK;
+}
+
+static int tiles_common(vcrt_ctx* c, int what, uint32_t rank, uint32_t count, void* packed, size_t bytes, bool pack) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "tiles: no storage images bound");
+    if (what != 0 && what != 2) return fail(c, VCRT_ERR_INVALID, "tiles: only the rgba8 target (0) and the f32 accumulation (2) are tile-packed");
+    if (count == 0) count = 1;
+    if (rank >= count) return fail(c, VCRT_ERR_INVALID, "tiles: tile_rank >= tile_count");
+    const uint32_t tiles = ((c->W + 31) / 32) * ((c->H + 31) / 32);
+    const uint32_t owned = tiles > rank ? (tiles - rank + count - 1) / count : 0u;
+    const size_t elem = what == 0 ? 4 : 16;
+    if (!packed || bytes < (size_t)owned * 1024u * elem) return fail(c, VCRT_ERR_INVALID, "tiles: packed buffer smaller than owned_tiles * 1024 * element size");
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, launch_tiles(what == 0 ? c->target.ptr : c->accumf.ptr, packed, (int)elem, pack, c->W, c->H, rank, count, owned, c->stream), "launch tile kernel");
+    c->launches += owned ? 1 : 0;
+    return VCRT_OK;
+}
+
+int vcrt_pack_tiles(vcrt_ctx* c, int what, uint32_t tile_rank, uint32_t tile_count, void* packed_dev, size_t bytes) {
+    return tiles_common(c, what, tile_rank, tile_count, packed_dev, bytes, true);
+}
+int vcrt_unpack_tiles(vcrt_ctx* c, int what, uint32_t tile_rank, uint32_t tile_count, const void* packed_dev, size_t bytes) {
+    return tiles_common(c, what, tile_rank, tile_count, const_cast<void*>(packed_dev), bytes, false);
 }
 
 static int read_common(vcrt_ctx* c, const DevBuf& b, void* dst, size_t bytes, const char* what) {

@@ -63,5 +63,6 @@ cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, in
 cudaError_t launch_render_reference(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_fast(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_brute(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
+cudaError_t launch_tiles(void* image, void* packed, int elem_bytes, bool pack, uint32_t W, uint32_t H, uint32_t rank, uint32_t count, uint32_t owned, cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accumf, uchar4* target, uint32_t npix, float inv_total, float inv_gamma, cudaStream_t stream);
 }  // namespace vcrt

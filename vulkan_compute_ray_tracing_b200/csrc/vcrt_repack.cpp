@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <omp.h>
 
 namespace vcrt {
 
@@ -207,6 +208,8 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err) {
     fb.depth = sb.max_depth.load();
     return true;
 }
+
+void set_repack_threads(int n) { omp_set_num_threads(n < 1 ? 1 : n); }
 
 // ------------------------------------------------------------------------------------------ quantisation
 bool quantize_fast_bvh(FastBvh& fb, float max_quantum) {

@@ -39,4 +39,7 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err);
 // beyond that the 64-byte float nodes are kept.  Returns whether the quantised form was produced.
 bool quantize_fast_bvh(FastBvh& fb, float max_quantum);
 
+// OpenMP threads used by the functions above (process-wide).
+void set_repack_threads(int n);
+
 }  // namespace vcrt

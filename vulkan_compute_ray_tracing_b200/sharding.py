@@ -106,6 +106,27 @@ def gather_tiles(packed, width, height, world, out_flat, group=None):
     return out_flat
 
 
+def gather_tiles_device(material, what, rank, world, group=None):
+    """Tile-sharded frame -> complete frame on every rank, on the GPU: vcrt_pack_tiles (CUDA) -> NCCL all_gather of the
+    equally sized packed buffers -> vcrt_unpack_tiles (CUDA) of every peer's tiles into this rank's image.
+    what: 0 rgba8 target, 2 f32 accumulation.  Everything is enqueued on torch's current stream, which must be the
+    stream the material renders on (ComputeMaterial.setStream)."""
+    import torch
+    import torch.distributed as dist
+    img = material.getStorageImages()[0].data
+    elem = 4 if what == 0 else 16
+    n = max_owned_tiles(img.width, img.height, world) * TILE * TILE * elem
+    mine = torch.empty(n, dtype=torch.uint8, device="cuda")
+    material.packTiles(what, rank, world, mine.data_ptr(), n)
+    if world == 1:
+        return
+    everyone = torch.empty(world * n, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(everyone, mine, group=group)
+    for r in range(world):
+        if r != rank:
+            material.unpackTiles(what, r, world, everyone.data_ptr() + r * n, n)
+
+
 def render_sharded(render, params, mode, rank, world, total_samples=None, group=None, dst=0):
     """render(params) must add this rank's samples into its accumulation tensor ((H, W, 4) f32, zeroed by the caller
     beforehand) and return it.  After the call rank `dst` holds the combined sums."""
