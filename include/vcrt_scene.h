@@ -32,6 +32,15 @@ uint32_t vcrt_scene_collect_lights(const vcrt_triangle* triangles, uint32_t n, c
 uint32_t vcrt_scene_generate_box(uint32_t target_triangles, uint32_t seed, vcrt_triangle* triangles, uint32_t max_triangles,
                                  vcrt_material* materials, uint32_t max_materials, uint32_t* num_materials);
 
+/* OBJ ingestion as the reference's path tracer sees it (Mesh::Mesh, mesh.cpp:96-139 through tinyobjloader, then
+ * getTriangles, RtScene.h:13-30): positions of the face corners, faces in file order, polygons fanned around their first
+ * corner, everything else in the file ignored; every triangle gets `material_index`.  Returns the triangle count (0 with
+ * vcrt_scene_last_error() set on failure); `out` may be NULL to query the count. */
+uint32_t vcrt_scene_load_obj(const char* path, uint32_t material_index, vcrt_triangle* out, uint32_t max_triangles);
+
+/* The six materials of RtScene.h:48-60 (gray, red, green, white light, metal, glass).  Returns 6. */
+uint32_t vcrt_scene_default_materials(vcrt_material* out, uint32_t max_materials);
+
 /* glibc rand() (TYPE_3 additive feedback), for tests: writes n outputs of the sequence after srand(seed). */
 void vcrt_scene_glibc_rand(uint32_t seed, uint32_t n, int32_t* out);
 

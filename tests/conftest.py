@@ -56,6 +56,13 @@ def doge():
     return load_scene(os.path.join(GOLDEN, "doge_scene.vcrt"))
 
 
+@pytest.fixture(scope="session")
+def doge_glass():
+    """Bundled scene + box1.obj as glass + box2.obj as metal (tests/golden/make_golden.py)."""
+    from refharness import load_scene
+    return load_scene(os.path.join(GOLDEN, "doge_glass_scene.vcrt"))
+
+
 def load_png(name):
     from PIL import Image
     return np.array(Image.open(os.path.join(GOLDEN, name)).convert("RGBA"))

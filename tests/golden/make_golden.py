@@ -9,6 +9,11 @@ Outputs (all small, committed):
                                    RtScene.h/Bvh.h/mesh.cpp (oracle/_ref/ref_scene_dump)
   ref_<variant>_800x600_f<N>.png   rgba8 target image after N frames of the reference frame loop (dispatch + copy),
                                    camera main.cpp:37, full-cover dispatch (25 x 19 groups)
+  doge_glass_scene.vcrt            BASELINE config 2's scene variant: the bundled scene plus box1.obj as glass (material 5) and
+                                   box2.obj as metal (material 4) -- the meshes RtScene.h:67,69 keeps commented out -- assembled by
+                                   the product's scene library (vcrt_scene_load_obj / vcrt_scene_build_bvh), whose output for the
+                                   default scene is checked to equal ref_scene_dump's bit for bit
+  ref_glass_full_b8_s16_800x600_f2.png   the reference shader's frame for that scene (depth 8, 2 frames)
   ref_hits.npz                     reference hit_bvh records for 4096 seeded rays (primary + random)
   ref_facts.json                   PCG stream KATs and primary-hit material histograms
 """
@@ -42,6 +47,17 @@ def main():
     img = ref.render_frames("full_b2_s16", scene, CAM, 800, 600, 2, lights_length=1)
     Image.fromarray(img, "RGBA").save(os.path.join(HERE, "ref_full_b2_s16_800x600_f2_lights1.png"), optimize=True)
 
+    # glass + metal variant (config 2), built by the product's scene library from the reference's OBJ files
+    sys.path.insert(0, root)
+    from vulkan_compute_ray_tracing_b200 import save_scene, scenegen
+    models = "/root/reference/resources/models/doge_scene"
+    again = scenegen.load_default_scene(models)
+    assert all(np.array_equal(again[k], scene[k]) for k in scene), "scene library differs from the reference's own scene dump"
+    glass = scenegen.load_default_scene(models, extra=(("box1.obj", 5), ("box2.obj", 4)))
+    save_scene(os.path.join(HERE, "doge_glass_scene.vcrt"), glass)
+    img = ref.render_frames("full_b8_s16", glass, CAM, 800, 600, 2)
+    Image.fromarray(img, "RGBA").save(os.path.join(HERE, "ref_glass_full_b8_s16_800x600_f2.png"), optimize=True)
+
     rs = np.random.RandomState(1234)
     n = 4096
     rays = np.zeros((n, 6), np.float32)
@@ -66,6 +82,10 @@ def main():
         hr = ref.hit_bvh("full_b2_s16", scene, rays)
         mats = np.where(hr[:, 0] == 1, hr[:, 1], 0xFFFFFFFF)
         facts["material_histogram"]["%dx%d" % (w, h)] = {str(int(m)): int((mats == m).sum()) for m in np.unique(mats)}
+    ys, xs = np.mgrid[0:600, 0:800]
+    hr = ref.hit_bvh("full_b8_s16", glass, primary_rays(800, 600, xs.ravel(), ys.ravel()))
+    mats = np.where(hr[:, 0] == 1, hr[:, 1], 0xFFFFFFFF)
+    facts["material_histogram"]["glass_800x600"] = {str(int(m)): int((mats == m).sum()) for m in np.unique(mats)}
     with open(os.path.join(HERE, "ref_facts.json"), "w") as f:
         json.dump(facts, f, indent=1, sort_keys=True)
     print(json.dumps(facts["material_histogram"]))

@@ -119,6 +119,30 @@ def test_c2_config_1080p(oracle, doge):
     assert [int((mats == m).sum()) for m in (0, 1, 2, 3)] == [425240, 112140, 20164, 5706]
 
 
+def test_c2_glass_scene_1080p(oracle, doge_glass):
+    """BASELINE config 2 in full: bundled scene + glass box + metal box, 1920x1080, depth 8, light sampling.  (a) the
+    reference shader's golden frame for this scene (800x600, 2 frames, rgba8 running mean) within 1 LSB (libm trig);
+    (b) 1080p, portable trig: f32 accumulation and primary hits bit-exact against the oracle on 4 of the 16 spp;
+    (c) the remaining 12 spp are covered by the slice property: 16 spp == 4 + 12 on the GPU."""
+    from gpuharness import GpuScene
+    g = GpuScene(doge_glass, 800, 600)
+    got = g.render(CAM, traversal="fast", shader="full", max_bounces=8, sample_count=2, accum="rgba8_ref", rng="pcg_ref", trig="libm")["target"]
+    g.close()
+    want = load_png("ref_glass_full_b8_s16_800x600_f2.png")
+    assert frac_within_1lsb(got, want) >= 0.999 and np.array_equal(got[..., 3], want[..., 3])
+    g = GpuScene(doge_glass, 1920, 1080)
+    kw = dict(shader="full", max_bounces=8, accum="f32", rng="philox", trig="portable", philox_seed=2)
+    a = oracle.render(doge_glass, CAM, 1920, 1080, make_params(sample_count=4, **kw), want_aov=True)
+    b = g.render(CAM, traversal="fast", want_aov=True, sample_count=4, **kw)
+    assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"])
+    mats = b["aov"]["material"]
+    assert int((mats == 5).sum()) > 100000 and int((mats == 4).sum()) > 40000      # glass and metal are in view
+    rest = g.render(CAM, traversal="fast", sample_begin=4, sample_count=12, clear=False, **kw)["accumf"]
+    full = g.render(CAM, traversal="fast", sample_count=16, **kw)["accumf"]
+    g.close()
+    assert same_bits(rest, full)
+
+
 def test_glass_metal_deep_tree(oracle):
     from gpuharness import GpuScene
     sc = small_scene(n_tris=5000, seed=5)

@@ -57,6 +57,18 @@ def test_oracle_reproduces_reference_frames(oracle, doge, name, kw):
     assert np.array_equal(got, want)
 
 
+def test_oracle_reproduces_reference_glass_scene_frame(oracle, doge_glass):
+    """BASELINE config 2's variant (glass box + metal box, depth 8): golden frame of the reference shader, bit-exact; the
+    primary-hit material histogram includes glass (5) and metal (4)."""
+    got = oracle.render(doge_glass, CAM, 800, 600, make_params(shader="full", max_bounces=8, sample_count=2), want_aov=True)
+    assert np.array_equal(got["target"], load_png("ref_glass_full_b8_s16_800x600_f2.png"))
+    want = FACTS["material_histogram"]["glass_800x600"]
+    mats = got["aov"]["material"]
+    for m in (0, 1, 2, 3, 4, 5):
+        assert int((mats == m).sum()) == want[str(m)]
+    assert want["5"] > 20000 and want["4"] > 9000
+
+
 def test_oracle_reproduces_reference_hit_records(oracle, doge):
     g = np.load(os.path.join(GOLDEN, "ref_hits.npz"))
     out, tri = oracle.hit_bvh(doge, g["rays"])

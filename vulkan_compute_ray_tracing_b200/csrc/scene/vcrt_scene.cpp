@@ -247,4 +247,74 @@ uint32_t vcrt_scene_generate_box(uint32_t target, uint32_t seed, vcrt_triangle* 
     return n;
 }
 
+
+// ---------------------------------------------------------------------------------------------- OBJ ingestion
+// What mesh.cpp:96-139 + RtScene.h:13-30 extract from an OBJ file: the positions of every face corner, faces in file
+// order, polygons fanned around their first corner (tinyobjloader's default triangulation; the bundled files hold triangles
+// only).  Texture coordinates, normals, groups and materials in the file are ignored, as they are by the reference's path
+// tracer.  Indices may be negative (relative).  Returns the triangle count; `out` may be NULL to query it.
+uint32_t vcrt_scene_load_obj(const char* path, uint32_t material_index, vcrt_triangle* out, uint32_t max_triangles) {
+    g_err.clear();
+    FILE* f = path ? std::fopen(path, "rb") : nullptr;
+    if (!f) { g_err = std::string("failed to open file: ") + (path ? path : "(null)"); return 0; }
+    std::vector<float> pos;
+    std::vector<char> line(1 << 16);
+    uint32_t n = 0;
+    bool bad = false;
+    while (std::fgets(line.data(), (int)line.size(), f)) {
+        const char* p = line.data();
+        while (*p == ' ' || *p == '\t') ++p;
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
+            char* e = nullptr;
+            p += 2;
+            for (int k = 0; k < 3; ++k) { pos.push_back((float)std::strtod(p, &e)); if (e == p) bad = true; p = e; }
+        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
+            p += 2;
+            long idx[64];
+            int cnt = 0;
+            for (;;) {
+                while (*p == ' ' || *p == '\t') ++p;
+                if (*p == 0 || *p == '\n' || *p == '\r') break;
+                char* e = nullptr;
+                long v = std::strtol(p, &e, 10);
+                if (e == p) { bad = true; break; }
+                const long nv = (long)(pos.size() / 3);
+                v = v < 0 ? nv + v : v - 1;
+                if (v < 0 || v >= nv) { bad = true; break; }
+                if (cnt < 64) idx[cnt++] = v;
+                p = e;
+                while (*p && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r') ++p;   // skip /vt/vn
+            }
+            for (int k = 1; k + 1 < cnt; ++k) {
+                if (out && n < max_triangles) {
+                    vcrt_triangle t;
+                    std::memset(&t, 0, sizeof t);
+                    std::memcpy(t.v0, &pos[3 * idx[0]], 12); std::memcpy(t.v1, &pos[3 * idx[k]], 12); std::memcpy(t.v2, &pos[3 * idx[k + 1]], 12);
+                    t.materialIndex = material_index;
+                    out[n] = t;
+                }
+                ++n;
+            }
+        }
+        if (bad) break;
+    }
+    std::fclose(f);
+    if (bad) { g_err = std::string("failed to parse OBJ: ") + path; return 0; }
+    if (n == 0) g_err = std::string("failed to load OBJ: no faces in ") + path;
+    return n;
+}
+
+// The material table of RtScene.h:48-60: gray, red, green, white light (2,2,2), metal, glass.
+uint32_t vcrt_scene_default_materials(vcrt_material* out, uint32_t max_materials) {
+    static const struct { uint32_t type; float a[3]; } tab[6] = {
+        {VCRT_MAT_LAMBERTIAN, {0.3f, 0.3f, 0.3f}}, {VCRT_MAT_LAMBERTIAN, {0.9f, 0.1f, 0.1f}}, {VCRT_MAT_LAMBERTIAN, {0.1f, 0.9f, 0.1f}},
+        {VCRT_MAT_LIGHT, {2.0f, 2.0f, 2.0f}}, {VCRT_MAT_METAL, {1.0f, 1.0f, 1.0f}}, {VCRT_MAT_GLASS, {1.0f, 1.0f, 1.0f}}};
+    for (uint32_t i = 0; i < 6 && out && i < max_materials; ++i) {
+        std::memset(&out[i], 0, sizeof out[i]);
+        out[i].type = tab[i].type;
+        std::memcpy(out[i].albedo, tab[i].a, 12);
+    }
+    return 6;
+}
+
 }  // extern "C"
