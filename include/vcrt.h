@@ -139,6 +139,13 @@ int vcrt_render(vcrt_ctx* ctx, const vcrt_render_params* params);
 int vcrt_clear_accum(vcrt_ctx* ctx);                                /* zero target, accumulation, f32 accumulation, AOV */
 int vcrt_resolve(vcrt_ctx* ctx, uint32_t total_samples, float gamma); /* f32 accumulation / total -> clamp -> pow(1/gamma) -> target rgba8 (gamma<=0: none; 2.2 = post-process-shader.frag:67-68) */
 
+/* The reference's post-process pass (resources/shaders/source/post-process-shader.frag:26-70) on the rgba8 target, into a
+ * ctx-owned rgba8 "present" image (what the reference draws to the swapchain): out.rgb = pow(mix * smartDeNoise(target, sigma,
+ * kSigma, threshold) + (1 - mix) * target, 1/gamma), out.a = 1.  mix = 0 and gamma = 2.2 is the shipped shader (the denoiser
+ * call is commented out, :64-65, where it would run with mix 0.5, sigma 2, kSigma 2, threshold 0.05); gamma <= 0: none. */
+int vcrt_post_process(vcrt_ctx* ctx, float mix, float sigma, float k_sigma, float threshold, float gamma);
+int vcrt_read_present_rgba8(vcrt_ctx* ctx, void* dst, size_t bytes);
+
 /* Read-backs (synchronise ctx's stream).  bytes must equal the buffer size. */
 int vcrt_read_target_rgba8(vcrt_ctx* ctx, void* dst, size_t bytes); /* getStorageImages()[0], main.cpp:194 */
 int vcrt_read_accum_rgba8(vcrt_ctx* ctx, void* dst, size_t bytes);  /* getStorageImages()[1], main.cpp:195 */

@@ -501,3 +501,69 @@ void vcrt_oracle_random(uint32_t seed, int n, float* out) {
     g.pcg = seed;
     for (int i = 0; i < n; ++i) out[i] = rng_next(&g);
 }
+
+/* ---------------------------------------------------------------- post-process pass
+ * post-process-shader.frag:26-70 restated: smartDeNoise (:26-60; commented out of main at :64) blended with the plain
+ * texel by `mix`, then pow(rgb, 1/gamma), alpha 1 (:67-68).  `tex` is the rgba8 target sampled as the reference's sampler
+ * does (Image.cpp:353-364): normalised texels, LINEAR filter, REPEAT addressing.  The full-screen quad puts fragment
+ * (px, py) at texel centre (px, py); the kernel offsets are integral in x and fractional in y (y starts at -sqrt(r^2-x^2)),
+ * so only the y direction interpolates.  Canonical filter arithmetic: fp32, weight = frac(y), a*(1-w) + b*w. */
+static inline void texel(const uint8_t* tex, int w, int h, int x, int y, float out[4]) {
+    x %= w; if (x < 0) x += w;
+    y %= h; if (y < 0) y += h;
+    const uint8_t* p = tex + 4 * ((size_t)y * w + x);
+    for (int c = 0; c < 4; ++c) out[c] = (float)p[c] / 255.0f;
+}
+
+static inline void sample_linear_y(const uint8_t* tex, int w, int h, int x, float y, float out[4]) {
+    float fy = floorf(y);
+    float wy = y - fy;
+    float a[4], b[4];
+    texel(tex, w, h, x, (int)fy, a);
+    texel(tex, w, h, x, (int)fy + 1, b);
+    for (int c = 0; c < 4; ++c) out[c] = a[c] * (1.0f - wy) + b[c] * wy;
+}
+
+int vcrt_oracle_post_process(const uint8_t* tex, uint32_t width, uint32_t height, float mix, float sigma, float kSigma, float threshold,
+                             float gamma, uint8_t* out) {
+    if (!tex || !out || width == 0 || height == 0) return VCRT_ERR_INVALID;
+    const int w = (int)width, h = (int)height;
+    const float INV_SQRT_OF_2PI = 0.39894228040143267793994605993439f, INV_PI = 0.31830988618379067153776752674503f;
+#pragma omp parallel for schedule(static)
+    for (int py = 0; py < h; ++py)
+        for (int px = 0; px < w; ++px) {
+            float centr[4];
+            texel(tex, w, h, px, py, centr);
+            float col[4] = {centr[0], centr[1], centr[2], centr[3]};
+            if (mix != 0.0f) {
+                float radius = roundf(kSigma * sigma);
+                float radQ = radius * radius;
+                float invSigmaQx2 = 0.5f / (sigma * sigma);
+                float invSigmaQx2PI = INV_PI * invSigmaQx2;
+                float invThresholdSqx2 = 0.5f / (threshold * threshold);
+                float invThresholdSqrt2PI = INV_SQRT_OF_2PI / threshold;
+                float zBuff = 0.0f, aBuff[4] = {0, 0, 0, 0};
+                for (float x = -radius; x <= radius; x += 1.0f) {
+                    float pt = sqrtf(radQ - x * x);
+                    for (float y = -pt; y <= pt; y += 1.0f) {
+                        float blurFactor = expf(-(x * x + y * y) * invSigmaQx2) * invSigmaQx2PI;
+                        float walk[4];
+                        sample_linear_y(tex, w, h, px + (int)x, (float)py + y, walk);
+                        float dC[4] = {walk[0] - centr[0], walk[1] - centr[1], walk[2] - centr[2], walk[3] - centr[3]};
+                        float dd = ((dC[0] * dC[0] + dC[1] * dC[1]) + dC[2] * dC[2]) + dC[3] * dC[3];
+                        float deltaFactor = expf(-dd * invThresholdSqx2) * invThresholdSqrt2PI * blurFactor;
+                        zBuff += deltaFactor;
+                        for (int c = 0; c < 4; ++c) aBuff[c] += deltaFactor * walk[c];
+                    }
+                }
+                for (int c = 0; c < 4; ++c) col[c] = mix * (aBuff[c] / zBuff) + (1.0f - mix) * centr[c];
+            }
+            uint8_t* o = out + 4 * ((size_t)py * w + px);
+            for (int c = 0; c < 3; ++c) {
+                float v = gamma > 0.0f ? powf(col[c], 1.0f / gamma) : col[c];
+                o[c] = unorm8(v);
+            }
+            o[3] = 255;
+        }
+    return VCRT_OK;
+}

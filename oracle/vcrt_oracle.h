@@ -35,6 +35,10 @@ int vcrt_oracle_render(const vcrt_oracle_scene* scene, const vcrt_ubo* ubo, cons
 
 int vcrt_oracle_hit_bvh(const vcrt_oracle_scene* scene, uint32_t stack_depth, const float* org_dir6, int n,
                         uint32_t* out10, int32_t* tri_out);
+/* post-process-shader.frag:26-70: mix * smartDeNoise(sigma, kSigma, threshold) + (1-mix) * texel, then pow(rgb, 1/gamma)
+ * (gamma <= 0: none), alpha 1.  tex/out: rgba8 W*H. */
+int vcrt_oracle_post_process(const uint8_t* tex, uint32_t width, uint32_t height, float mix, float sigma, float kSigma, float threshold,
+                             float gamma, uint8_t* out);
 void vcrt_oracle_random(uint32_t seed, int n, float* out);
 uint32_t vcrt_oracle_pcg_next(uint32_t* state);
 void vcrt_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

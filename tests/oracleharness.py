@@ -112,6 +112,16 @@ class Oracle:
             raise RuntimeError("vcrt_oracle_render failed: %d" % rc)
         return dict(target=target, accum8=accum8, accumf=accumf, aov=aov, counters=cnt)
 
+    def post_process(self, tex, mix=0.0, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2):
+        tex = np.ascontiguousarray(tex, np.uint8)
+        h, w = tex.shape[:2]
+        out = np.zeros_like(tex)
+        fn = self.lib.vcrt_oracle_post_process
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        assert fn(tex.ctypes.data, w, h, mix, sigma, k_sigma, threshold, gamma, out.ctypes.data) == 0
+        return out
+
     def hit_bvh(self, scene, org_dir, stack_depth=16):
         org_dir = np.ascontiguousarray(org_dir, np.float32)
         n = org_dir.shape[0]

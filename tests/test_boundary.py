@@ -101,3 +101,17 @@ def test_binding_order_and_shader_names():
     assert m.getStorageImages() == [] and m.getStorageBufferBundles() == []
     with pytest.raises(vcrt.VcrtError, match="failed to"):
         m.bind(None, 0)
+
+
+def test_camera_matches_reference_defaults():
+    """Camera.h:28-134 restated: yaw 180 / pitch 0 looks down -x; W/S/A/D/UP/DOWN move by SPEED * dt along Front/Right/Up."""
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    c = vcrt.Camera()
+    assert np.allclose(c.Front, (-1, 0, 0), atol=1e-6) and np.allclose(c.Right, (0, 0, -1), atol=1e-6) and np.allclose(c.Up, (0, 1, 0), atol=1e-6)
+    p0 = c.Position.copy()
+    c.ProcessKeyboard("w", 0.1)
+    assert np.allclose(c.Position - p0, (-0.25, 0, 0), atol=1e-6)
+    c.ProcessKeyboard("d", 0.1); c.ProcessKeyboard("u", 0.2)
+    assert np.allclose(c.Position - p0, (-0.25, 0.5, -0.25), atol=1e-6)
+    c.ProcessKeyboard(".", 1.0)
+    assert np.allclose(c.Position - p0, (-0.25, 0.5, -0.25), atol=1e-6)

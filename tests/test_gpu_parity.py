@@ -136,7 +136,7 @@ def test_c2_glass_scene_1080p(oracle, doge_glass):
     b = g.render(CAM, traversal="fast", want_aov=True, sample_count=4, **kw)
     assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"])
     mats = b["aov"]["material"]
-    assert int((mats == 5).sum()) > 100000 and int((mats == 4).sum()) > 40000      # glass and metal are in view
+    assert int((mats == 5).sum()) > 60000 and int((mats == 4).sum()) > 20000      # glass and metal are in view
     rest = g.render(CAM, traversal="fast", sample_begin=4, sample_count=12, clear=False, **kw)["accumf"]
     full = g.render(CAM, traversal="fast", sample_count=16, **kw)["accumf"]
     g.close()
@@ -382,3 +382,39 @@ def test_two_gpus_match_one(mode):
                 p.terminate()
             assert p.exitcode == 0
         assert dict(out) == {0: True, 1: True}
+
+
+def test_post_process_matches_oracle(gpu_doge, oracle):
+    """vcrt_post_process (CUDA) vs the restated fragment shader: gamma-only exactly as shipped, and with smartDeNoise enabled
+    as its commented-out call would (mix 0.5, sigma 2, kSigma 2, threshold 0.05).  expf/powf differ by ulps between CUDA and
+    glibc: <= 1 LSB on >= 99.9 % of channels, never more than 2."""
+    gpu_doge.material.clearAccum()
+    img = gpu_doge.frames(CAM, 3)
+    for kw in (dict(mix=0.0, gamma=2.2), dict(mix=0.5, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2), dict(mix=1.0, sigma=3.0, k_sigma=2.0, threshold=0.2, gamma=0.0)):
+        got = gpu_doge.material.postProcess(**kw)
+        want = oracle.post_process(img, **kw)
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert (d <= 1).mean() >= 0.999 and d.max() <= 2, kw
+        assert (got[..., 3] == 255).all()
+    with pytest.raises(Exception):
+        gpu_doge.material.postProcess(mix=0.5, sigma=0.0)
+
+
+def test_scripted_frame_loop(oracle, doge):
+    """The reference's frame loop with a scripted keyboard (frameloop.py): accumulation restarts on every camera move
+    (main.cpp:169-173), so after "..w.." the target holds frames 0..2 of the moved camera -- checked against the oracle."""
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 320, 240)
+    loop = vcrt.FrameLoop(g.model, doge, 320, 240, frame_time=0.5)
+    img = loop.run("...")
+    want = oracle.render(doge, CAM, 320, 240, make_params(sample_count=3))["target"]
+    assert frac_within_1lsb(img, want) >= 0.999
+    img = loop.run("w..")
+    cam = tuple(float(x) for x in loop.camera.Position)
+    assert cam != tuple(CAM) and loop.currentSample == 3 and loop.frames == 6
+    want = oracle.render(doge, cam, 320, 240, make_params(sample_count=3))["target"]
+    assert frac_within_1lsb(img, want) >= 0.999
+    with pytest.raises(ValueError):
+        loop.run("x")
+    g.close()

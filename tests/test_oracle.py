@@ -132,3 +132,19 @@ def test_oracle_modes_consistency(oracle, doge):
     assert all((p[..., 3] > 0).sum() > 0 for p in parts)
     cover = sum((p[..., 3] > 0).astype(int) for p in parts)
     assert cover.max() == 1 and cover.min() == 1
+
+
+def test_post_process_restatement(oracle, doge):
+    """post-process-shader.frag restated: gamma-only path (the shipped shader) against numpy; smartDeNoise keeps flat
+    regions, smooths Monte-Carlo noise and leaves hard edges in place."""
+    img = oracle.render(doge, CAM, 200, 150, make_params(shader="full", sample_count=2))["target"]
+    out = oracle.post_process(img, mix=0.0, gamma=2.2)
+    want = np.rint(np.clip((img[..., :3] / np.float32(255.0)) ** np.float32(1 / 2.2), 0, 1) * 255.0)
+    assert np.abs(out[..., :3].astype(int) - want.astype(int)).max() <= 1 and (out[..., 3] == 255).all()
+    assert np.array_equal(oracle.post_process(img, mix=0.0, gamma=0.0)[..., :3], img[..., :3])
+    flat = np.full((40, 50, 4), 77, np.uint8)
+    assert np.array_equal(oracle.post_process(flat, mix=0.5, gamma=0.0)[..., :3], flat[..., :3])
+    den = oracle.post_process(img, mix=1.0, sigma=2.0, k_sigma=2.0, threshold=0.3, gamma=0.0)
+    lit = img[..., :3].astype(float).sum(-1) > 0
+    rough = lambda a: np.abs(np.diff(a[..., :3].astype(float), axis=1))[lit[:, 1:] & lit[:, :-1]].mean()
+    assert rough(den) < 0.8 * rough(img)

@@ -48,6 +48,8 @@ SIGNATURES = {
     "vcrt_render": (C.c_int, [_P, C.POINTER(RenderParams)]),
     "vcrt_clear_accum": (C.c_int, [_P]),
     "vcrt_resolve": (C.c_int, [_P, C.c_uint32, C.c_float]),
+    "vcrt_post_process": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "vcrt_read_present_rgba8": (C.c_int, [_P, _P, C.c_size_t]),
     "vcrt_read_target_rgba8": (C.c_int, [_P, _P, C.c_size_t]),
     "vcrt_read_accum_rgba8": (C.c_int, [_P, _P, C.c_size_t]),
     "vcrt_read_accum_f32": (C.c_int, [_P, _P, C.c_size_t]),

@@ -221,6 +221,16 @@ class ComputeMaterial:
         self._require()
         self._check(N.lib().vcrt_resolve(self._ctx, int(total_samples), float(gamma)))
 
+    def postProcess(self, mix=0.0, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2):
+        """post-process-shader.frag on the target image -> (H, W, 4) uint8 present image.  Defaults = the shipped shader
+        (denoiser off, gamma 2.2); mix=0.5 enables smartDeNoise as its commented-out call would (:64)."""
+        self._require()
+        self._check(N.lib().vcrt_post_process(self._ctx, mix, sigma, k_sigma, threshold, gamma))
+        t = self.m_storageImageDescriptors[0].data
+        out = np.empty((t.height, t.width, 4), np.uint8)
+        self._check(N.lib().vcrt_read_present_rgba8(self._ctx, out.ctypes.data, out.nbytes))
+        return out
+
     def devicePtr(self, what):
         """(pointer, bytes) of a ctx-owned image: 0 target rgba8, 1 accumulation rgba8, 2 f32 accumulation, 3 AOV."""
         self._require()

@@ -47,7 +47,7 @@ struct vcrt_ctx {
     int32_t froot = (int32_t)0x80000000;
     uint32_t nfnodes = 0;
     uint32_t W = 0, H = 0;
-    DevBuf target, accum8, accumf, aov;
+    DevBuf target, accum8, accumf, aov, present;
     vcrt_ubo ubo;
     unsigned long long* d_counters = nullptr;   // rays, nodes, tris, work counter
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -189,7 +189,7 @@ int vcrt_destroy(vcrt_ctx* c) {
     for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c->trace_timer.destroy();
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
-    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes}) if (b->ptr) cudaFree(b->ptr);
+    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes, &c->present}) if (b->ptr) cudaFree(b->ptr);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -241,7 +241,7 @@ int vcrt_set_buffer_device(vcrt_ctx* c, int binding, const void* dev, size_t byt
 int vcrt_clear_accum(vcrt_ctx* c) {
     if (!c) return VCRT_ERR_INVALID;
     CU(c, cudaSetDevice(c->device), "set device");
-    for (DevBuf* b : {&c->target, &c->accum8, &c->accumf, &c->aov})
+    for (DevBuf* b : {&c->target, &c->accum8, &c->accumf, &c->aov, &c->present})
         if (b->ptr && b->bytes) CU(c, cudaMemsetAsync(b->ptr, 0, b->bytes, c->stream), "clear image");
     return VCRT_OK;
 }
@@ -253,7 +253,8 @@ int vcrt_set_image_size(vcrt_ctx* c, uint32_t w, uint32_t h) {
     const size_t npix = (size_t)w * h;
     int rc;
     if ((rc = ensure(c, c->target, npix * 4, "allocate target image")) || (rc = ensure(c, c->accum8, npix * 4, "allocate accumulation image")) ||
-        (rc = ensure(c, c->accumf, npix * 16, "allocate f32 accumulation")) || (rc = ensure(c, c->aov, npix * sizeof(vcrt_aov), "allocate AOV buffer")))
+        (rc = ensure(c, c->accumf, npix * 16, "allocate f32 accumulation")) || (rc = ensure(c, c->aov, npix * sizeof(vcrt_aov), "allocate AOV buffer")) ||
+        (rc = ensure(c, c->present, npix * 4, "allocate present image")))
         return rc;
     c->W = w; c->H = h;
     return vcrt_clear_accum(c);
@@ -402,6 +403,18 @@ int vcrt_resolve(vcrt_ctx* c, uint32_t total_samples, float gamma) {
     return VCRT_OK;
 }
 
+int vcrt_post_process(vcrt_ctx* c, float mix, float sigma, float k_sigma, float threshold, float gamma) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_post_process: no storage images bound");
+    if (mix != 0.0f && (!(sigma > 0.0f) || !(k_sigma >= 0.0f) || !(threshold > 0.0f) || k_sigma * sigma > 64.0f))
+        return fail(c, VCRT_ERR_INVALID, "vcrt_post_process: need sigma > 0, kSigma >= 0, threshold > 0, kSigma * sigma <= 64");
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, launch_post_process((const uchar4*)c->target.ptr, (uchar4*)c->present.ptr, c->W, c->H, mix, sigma, k_sigma, threshold, gamma > 0.0f ? 1.0f / gamma : 0.0f, c->stream),
+       "launch post-process kernel");
+    c->launches += 1;
+    return VCRT_OK;
+}
+
 static int tiles_common(vcrt_ctx* c, int what, uint32_t rank, uint32_t count, void* packed, size_t bytes, bool pack) {
     if (!c) return VCRT_ERR_INVALID;
     if (c->W == 0) return fail(c, VCRT_ERR_STATE, "tiles: no storage images bound");
@@ -438,6 +451,7 @@ static int read_common(vcrt_ctx* c, const DevBuf& b, void* dst, size_t bytes, co
 int vcrt_read_target_rgba8(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->target, dst, bytes, "read target image") : VCRT_ERR_INVALID; }
 int vcrt_read_accum_rgba8(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->accum8, dst, bytes, "read accumulation image") : VCRT_ERR_INVALID; }
 int vcrt_read_accum_f32(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->accumf, dst, bytes, "read f32 accumulation") : VCRT_ERR_INVALID; }
+int vcrt_read_present_rgba8(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->present, dst, bytes, "read present image") : VCRT_ERR_INVALID; }
 int vcrt_read_aov(vcrt_ctx* c, void* dst, size_t bytes) { return c ? read_common(c, c->aov, dst, bytes, "read AOV buffer") : VCRT_ERR_INVALID; }
 
 int vcrt_write_accum_f32(vcrt_ctx* c, const void* src, size_t bytes) {

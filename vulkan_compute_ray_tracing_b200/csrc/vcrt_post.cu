@@ -55,6 +55,64 @@ cudaError_t launch_tiles(void* image, void* packed, int elem_bytes, bool pack, u
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- post-process pass
+// post-process-shader.frag:26-70 on the rgba8 target: smartDeNoise (a bilateral filter over a disc of radius
+// round(kSigma*sigma); the shader ships with it commented out of main, :64) blended with the plain texel by `mix`, then
+// pow(rgb, 1/gamma), alpha 1.  Sampling follows the reference's sampler (Image.cpp:353-364: LINEAR, REPEAT): offsets are
+// integral in x and fractional in y, so a tap blends two vertically adjacent texels.  One thread per pixel; the taps of a
+// 16x16 block overlap almost completely, so the rgba8 reads are L1 hits.
+__device__ __forceinline__ float4 post_texel(const uchar4* __restrict__ tex, int w, int h, int x, int y) {
+    x %= w; if (x < 0) x += w;
+    y %= h; if (y < 0) y += h;
+    const uchar4 p = tex[(size_t)y * w + x];
+    return make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, (float)p.w / 255.0f);
+}
+
+__global__ void __launch_bounds__(256) post_process_kernel(const uchar4* __restrict__ tex, uchar4* __restrict__ out, int w, int h, float mix, float sigma,
+                                                           float kSigma, float threshold, float inv_gamma) {
+    const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (px >= w || py >= h) return;
+    const float4 centr = post_texel(tex, w, h, px, py);
+    float col[3] = {centr.x, centr.y, centr.z};
+    if (mix != 0.0f) {
+        const float radius = roundf(kSigma * sigma), radQ = radius * radius;
+        const float invSigmaQx2 = 0.5f / (sigma * sigma), invSigmaQx2PI = 0.31830988618379067153776752674503f * invSigmaQx2;
+        const float invThresholdSqx2 = 0.5f / (threshold * threshold), invThresholdSqrt2PI = 0.39894228040143267793994605993439f / threshold;
+        float zBuff = 0.0f, ax = 0.0f, ay = 0.0f, az = 0.0f;
+        for (float x = -radius; x <= radius; x += 1.0f) {
+            const float pt = sqrtf(radQ - x * x);
+            for (float y = -pt; y <= pt; y += 1.0f) {
+                const float blurFactor = expf(-(x * x + y * y) * invSigmaQx2) * invSigmaQx2PI;
+                const float sy = (float)py + y, fy = floorf(sy), wy = sy - fy;
+                const float4 a = post_texel(tex, w, h, px + (int)x, (int)fy), b = post_texel(tex, w, h, px + (int)x, (int)fy + 1);
+                const float4 walk = make_float4(a.x * (1.0f - wy) + b.x * wy, a.y * (1.0f - wy) + b.y * wy, a.z * (1.0f - wy) + b.z * wy, a.w * (1.0f - wy) + b.w * wy);
+                const float dx = walk.x - centr.x, dy = walk.y - centr.y, dz = walk.z - centr.z, dw = walk.w - centr.w;
+                const float deltaFactor = expf(-(((dx * dx + dy * dy) + dz * dz) + dw * dw) * invThresholdSqx2) * invThresholdSqrt2PI * blurFactor;
+                zBuff += deltaFactor;
+                ax += deltaFactor * walk.x; ay += deltaFactor * walk.y; az += deltaFactor * walk.z;
+            }
+        }
+        col[0] = mix * (ax / zBuff) + (1.0f - mix) * centr.x;
+        col[1] = mix * (ay / zBuff) + (1.0f - mix) * centr.y;
+        col[2] = mix * (az / zBuff) + (1.0f - mix) * centr.z;
+    }
+    uint8_t o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = inv_gamma > 0.0f ? powf(col[k], inv_gamma) : col[k];
+        v = !(v == v) ? 0.0f : (v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v));
+        o[k] = (uint8_t)rintf(v * 255.0f);
+    }
+    out[(size_t)py * w + px] = make_uchar4(o[0], o[1], o[2], 255);
+}
+
+cudaError_t launch_post_process(const uchar4* tex, uchar4* out, uint32_t w, uint32_t h, float mix, float sigma, float kSigma, float threshold, float inv_gamma,
+                                cudaStream_t stream) {
+    if (w == 0 || h == 0) return cudaSuccess;
+    post_process_kernel<<<dim3((w + 15) / 16, (h + 15) / 16), 256, 0, stream>>>(tex, out, (int)w, (int)h, mix, sigma, kSigma, threshold, inv_gamma);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(const float4* accumf, uchar4* target, uint32_t npix, float inv_total, float inv_gamma, cudaStream_t stream) {
     if (npix == 0) return cudaSuccess;
     resolve_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(accumf, target, npix, inv_total, inv_gamma);
