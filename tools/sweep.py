@@ -16,6 +16,7 @@ ap.add_argument("--triangles", type=int, default=1000000)
 ap.add_argument("--bounces", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--count", action="store_true")
+ap.add_argument("--trace", action="store_true", help="also print the trace kernel's own time")
 ap.add_argument("--flags", type=int, default=0, help="8 static kernel, 16 megakernel")
 ap.add_argument("opts", nargs="*")
 a = ap.parse_args()
@@ -43,4 +44,6 @@ for combo in itertools.product(*vals) if vals else [()]:
         if rep:
             best = max(best, c.rays / c.kernel_ms / 1e3)
     extra = " nodes/ray %.1f tris/ray %.2f" % (c.nodes / c.rays, c.triangles / c.rays) if a.count else ""
+    if a.trace:
+        extra += " trace %.2f ms in %d launches = %.0f Mrays/s" % (c.trace_ms, c.trace_launches, c.rays / max(c.trace_ms, 1e-9) / 1e3)
     print(dict(zip(keys, combo)), "%.0f Mrays/s (best of %d, %.1f ms)%s" % (best, a.reps, c.kernel_ms, extra), flush=True)
