@@ -53,7 +53,8 @@ extern "C" int hostemu_render(const void* tris, uint32_t ntris, const void* mats
             if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
             return -1;
         }
-        s.fnodes = (const float4*)fb.nodes.data(); s.ftris = (const float4*)fb.tris.data(); s.nfnodes = fb.num_nodes(); s.froot = fb.root;
+        precompute_triangles(fb);
+        s.fnodes = (const float4*)fb.nodes.data(); s.ftris = (const float4*)fb.tris64.data(); s.nfnodes = fb.num_nodes(); s.froot = fb.root;
         // test hooks: _reserved bit 1 keeps the 64-byte float nodes, bit 2 quantises whatever the scene extent
         if (!(p->_reserved & 2u) && quantize_fast_bvh(fb, (p->_reserved & 4u) ? 3.0e38f : 2.5e-4f)) {
             s.qnodes = (const Words8*)fb.qnodes.data();   // std::vector storage is 16-byte aligned; the host load is a plain copy

@@ -31,7 +31,7 @@ struct vcrt_ctx {
     DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
     std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
     bool fast_dirty = true;
-    uint32_t leaf_threshold = 4, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
+    uint32_t leaf_threshold = 6, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
     bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
     int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (quantised when the scene extent allows) | 1 "q15" | 2 "f32"
     bool quantized = false;
@@ -43,7 +43,7 @@ struct vcrt_ctx {
     DevBuf fnodes, ftris;
     DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues
     uint32_t wf_capacity = 0;
-    uint32_t wf_batch = 32u << 20;         // option "wf_batch_paths": paths per wavefront batch (queue memory = 120 B per path)
+    uint32_t wf_batch = 64u << 20;         // option "wf_batch_paths": paths per wavefront batch (queue memory = 120 B per path)
     int32_t froot = (int32_t)0x80000000;
     uint32_t nfnodes = 0;
     uint32_t W = 0, H = 0;
@@ -273,12 +273,13 @@ static int prepare_fast(vcrt_ctx* c) {
         c->fast_ok = build_fast_bvh((const vcrt_bvh_node*)c->host_bvh.data(), (uint32_t)(c->host_bvh.size() / sizeof(vcrt_bvh_node)),
                                     (const vcrt_triangle*)c->host_tris.data(), (uint32_t)(c->host_tris.size() / sizeof(vcrt_triangle)), fb, c->fast_err);
         if (c->fast_ok && c->fast_sah) c->fast_ok = rebuild_fast_bvh_sah(fb, c->fast_err);
+        if (c->fast_ok) precompute_triangles(fb);
         c->fast_dirty = false;
         if (c->fast_ok) {
             int rc;
-            if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris.size() * 4, "allocate repacked triangles"))) return rc;
+            if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris64.size() * 4, "allocate repacked triangles"))) return rc;
             if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
-            if (!fb.tris.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris.data(), fb.tris.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
+            if (!fb.tris64.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris64.data(), fb.tris64.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
             // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
             c->quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, c->fast_nodes == 1 ? 3.0e38f : 2.5e-4f);
             if (c->quantized) {

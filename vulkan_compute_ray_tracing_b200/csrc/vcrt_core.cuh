@@ -218,7 +218,7 @@ struct SceneView {
     uint32_t ntris, nmats, nbvh, nlights, nspheres;
     // repacked records for the fast traversal (vcrt_fast.cuh); null until built
     const float4* fnodes;   // 64 B per inner node
-    const float4* ftris;    // 48 B per triangle, leaf order
+    const float4* ftris;    // 64 B per triangle, leaf order: {v0, original index} {a, materialIndex} {b, -} {n, -}
     uint32_t nfnodes;
     int32_t froot;          // >= 0 inner node, < 0 leaf (~triangle slot), INT_MIN empty
     // 32-byte quantised inner nodes (vcrt_repack.h: quantize_fast_bvh); null = walk the 64-byte float nodes
@@ -255,6 +255,28 @@ VCRT_HD bool tri_test(float3 v0, float3 v1, float3 v2, const Ray& r, float& t) {
     float u = dot(q, b) * idet, v = dot(q, a) * idet;
     t = dot(n, p) * idet;
     return !(u < 0.0f || u > 1.0f || v < 0.0f || (u + v) > 1.0f);
+}
+
+// The same test on a repacked record that carries a = v0 - v1, b = v2 - v0, n = cross(b, a) (vcrt_repack.h:
+// precompute_triangles): identical operations, the ray-independent ones done once at upload.
+VCRT_HD bool tri_test_pre(float3 v0, float3 a, float3 b, float3 n, const Ray& r, float& t) {
+    float3 p = sub(v0, r.o);
+    float3 q = cross(p, r.d);
+    float idet = 1.0f / dot(r.d, n);
+    float u = dot(q, b) * idet, v = dot(q, a) * idet;
+    t = dot(n, p) * idet;
+    return !(u < 0.0f || u > 1.0f || v < 0.0f || (u + v) > 1.0f);
+}
+
+VCRT_HD void finish_triangle_hit_pre(float3 n, uint32_t mat, int tri, const Ray& r, float t, Hit& rec) {
+    rec.p = add(r.o, scale(r.d, t));
+    rec.normal = normalize(n);
+    rec.backFaceInt = dot(r.d, rec.normal) > 0.0f ? 1 : 0;
+    rec.normal = scale(rec.normal, (float)(1 - 2 * rec.backFaceInt));
+    rec.p = add(rec.p, scale(rec.normal, 0.0001f));
+    rec.t = t;
+    rec.materialIndex = mat;
+    rec.triangle = tri;
 }
 
 VCRT_HD void finish_triangle_hit(float3 v0, float3 v1, float3 v2, uint32_t mat, int tri, const Ray& r, float t, Hit& rec) {

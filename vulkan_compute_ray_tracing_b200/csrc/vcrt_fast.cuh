@@ -13,7 +13,9 @@
 //   inner node, 64 B:  {L.min.x L.max.x L.min.y L.max.y} {R.min.x R.max.x R.min.y R.max.y}
 //                      {L.min.z L.max.z R.min.z R.max.z} {childL childR - -}
 //                      child >= 0: inner node index;  child < 0: leaf, triangle slot = ~child;  empty: box (+inf,-inf)
-//   triangle, 48 B:    {v0.xyz, original index} {v1.xyz, materialIndex} {v2.xyz, -}   in reference DFS leaf order
+//   triangle, 64 B:    {v0.xyz, original index} {a.xyz, materialIndex} {b.xyz, -} {n.xyz, -}   in reference DFS leaf order;
+//                      a = v0 - v1, b = v2 - v0, n = cross(b, a): the ray-independent part of triIntersect, precomputed with
+//                      the shader's own fp32 operations (vcrt_repack.h: precompute_triangles); two 256-bit loads per test
 //   quantised inner node, 32 B (QN = 1; used when the scene extent allows, vcrt_repack.h): the same twelve bounds as
 //                      15-bit fixed point in a scene-wide frame, rounded outwards, + the two child codes; one 256-bit load.
 //                      Boxes only grow, so the visited set is a superset of the float nodes' and results are unchanged.
@@ -146,10 +148,12 @@ VCRT_HD void trav_inner_step_lean(TravState& t, const SceneView& s, int32_t* sta
 // Test the triangle of leaf code `leaf` (= ~slot) with the reference's arithmetic and tie rule.
 VCRT_HD void trav_leaf_test(TravState& t, const SceneView& s, const Ray& r, int32_t leaf) {
     const int32_t slot = ~leaf;
-    const float4* p = s.ftris + 3 * (size_t)slot;
-    const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
+    const Words8* p = (const Words8*)(s.ftris + 4 * (size_t)slot);
+    const Words8 lo = ldg8(p), hi = ldg8(p + 1);
+    const float3 v0 = f3(u2f(lo.w[0]), u2f(lo.w[1]), u2f(lo.w[2])), ea = f3(u2f(lo.w[4]), u2f(lo.w[5]), u2f(lo.w[6]));
+    const float3 eb = f3(u2f(hi.w[0]), u2f(hi.w[1]), u2f(hi.w[2])), n = f3(u2f(hi.w[4]), u2f(hi.w[5]), u2f(hi.w[6]));
     float tt;
-    if (tri_test(xyz(a), xyz(b), xyz(c), r, tt) && tt > VCRT_T_MIN && (tt < t.closest || (tt == t.closest && slot < t.best))) {
+    if (tri_test_pre(v0, ea, eb, n, r, tt) && tt > VCRT_T_MIN && (tt < t.closest || (tt == t.closest && slot < t.best))) {
         t.closest = tt;
         t.best = slot;
     }
@@ -157,9 +161,9 @@ VCRT_HD void trav_leaf_test(TravState& t, const SceneView& s, const Ray& r, int3
 
 VCRT_HD bool trav_finish(const TravState& t, const SceneView& s, const Ray& r, Hit& rec) {
     if (t.best < 0) return false;
-    const float4* p = s.ftris + 3 * (size_t)t.best;
-    const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
-    finish_triangle_hit(xyz(a), xyz(b), xyz(c), f2u(b.w), (int)f2u(a.w), r, t.closest, rec);
+    const float4* p = s.ftris + 4 * (size_t)t.best;
+    const float4 a = ldg4(p), b = ldg4(p + 1), d = ldg4(p + 3);
+    finish_triangle_hit_pre(xyz(d), f2u(b.w), (int)f2u(a.w), r, t.closest, rec);
     return true;
 }
 

@@ -209,6 +209,25 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err) {
     return true;
 }
 
+void precompute_triangles(FastBvh& fb) {
+    const uint32_t n = fb.num_slots();
+    fb.tris64.assign((size_t)n * 16, 0.0f);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        const float* t = &fb.tris[(size_t)i * 12];
+        float* o = &fb.tris64[(size_t)i * 16];
+        // volatile: each operation is rounded to fp32 on its own, whatever the host compiler's contraction settings
+        volatile float a[3], b[3], m[6];
+        for (int k = 0; k < 3; ++k) { a[k] = t[k] - t[4 + k]; b[k] = t[8 + k] - t[k]; }
+        // cross(b, a) = (b.y*a.z - a.y*b.z, b.z*a.x - a.z*b.x, b.x*a.y - a.x*b.y)   (glm::cross operation order)
+        m[0] = b[1] * a[2]; m[1] = a[1] * b[2]; m[2] = b[2] * a[0]; m[3] = a[2] * b[0]; m[4] = b[0] * a[1]; m[5] = a[0] * b[1];
+        o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; o[3] = t[3];
+        o[4] = a[0]; o[5] = a[1]; o[6] = a[2]; o[7] = t[7];
+        o[8] = b[0]; o[9] = b[1]; o[10] = b[2];
+        o[12] = m[0] - m[1]; o[13] = m[2] - m[3]; o[14] = m[4] - m[5];
+    }
+}
+
 void set_repack_threads(int n) { omp_set_num_threads(n < 1 ? 1 : n); }
 
 // ------------------------------------------------------------------------------------------ quantisation

@@ -85,6 +85,9 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
     t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = EMPTY; t.sp = 0;
     t.selx = t.sely = t.selz = VCRT_Q15_SEL_LO;
     int32_t pending = EMPTY;
+#if VCRT_PEND_DEPTH == 2
+    int32_t pending2 = EMPTY;
+#endif
     int32_t stack[VCRT_FAST_STACK];
     stack[0] = EMPTY;                    // sentinel: popping an exhausted stack yields EMPTY
     TraceStats st = {0u, 0u, 0u};
@@ -121,20 +124,21 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                 if (COUNT) st.nodes++;
                 trav_inner_step_lean<QN>(t, s, stack);
             }
-            // a lane that arrives at a leaf postpones it (once) and keeps traversing
+            // a lane that arrives at a leaf postpones it (up to VCRT_PEND_DEPTH leaves) and keeps traversing
             bool at_leaf = (uint32_t)t.node > 0x80000000u;          // negative and not EMPTY
-            if (at_leaf && pending == EMPTY) {
-                pending = t.node;
-#if VCRT_PREFETCH >= 1
-                {   // the triangle is tested some iterations from now: start pulling its record (48 B, may straddle two lines) into L1
-                    const char* tp = (const char*)(s.ftris + 3 * (size_t)(~pending));
-                    prefetch_l1(tp);
-                    prefetch_l1(tp + 47);
-                }
-#endif
+#if VCRT_PEND_DEPTH == 2
+            if (at_leaf && pending2 == EMPTY) {
+                if (pending == EMPTY) pending = t.node; else pending2 = t.node;
                 t.node = stack[--t.sp];
                 at_leaf = (uint32_t)t.node > 0x80000000u;
             }
+#else
+            if (at_leaf && pending == EMPTY) {
+                pending = t.node;
+                t.node = stack[--t.sp];
+                at_leaf = (uint32_t)t.node > 0x80000000u;
+            }
+#endif
             const bool inner = t.node >= 0;
             const unsigned mi = __ballot_sync(FULL, inner);
             const unsigned mb = __ballot_sync(FULL, !inner && pending != EMPTY);   // cannot go on without the leaf phase
@@ -144,16 +148,25 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                 if (pending != EMPTY) {
                     if (COUNT) st.tris++;
                     trav_leaf_test(t, s, cur, pending);
+#if VCRT_PEND_DEPTH == 2
+                    pending = pending2;
+                    pending2 = EMPTY;
+#else
                     pending = EMPTY;
-                    if (at_leaf) {   // the leaf it was blocked on becomes the postponed one
-                        pending = t.node;
-#if VCRT_PREFETCH >= 1
-                        const char* tp = (const char*)(s.ftris + 3 * (size_t)(~pending));
-                        prefetch_l1(tp);
-                        prefetch_l1(tp + 47);
 #endif
-                        t.node = stack[--t.sp];
+                }
+#if VCRT_PEND_DEPTH == 2
+                if (__any_sync(FULL, pending != EMPTY)) {   // second postponed leaves
+                    if (pending != EMPTY) {
+                        if (COUNT) st.tris++;
+                        trav_leaf_test(t, s, cur, pending);
+                        pending = EMPTY;
                     }
+                }
+#endif
+                if (at_leaf) {   // the leaf the lane was blocked on becomes the postponed one
+                    pending = t.node;
+                    t.node = stack[--t.sp];
                 }
                 continue;
             }
