@@ -31,6 +31,7 @@ struct vcrt_ctx {
     DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
     std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
     bool fast_dirty = true;
+    uint32_t continue_threshold = 20;   // option "continue_threshold" (33 - min(leaf, shade) leaves the schedule unchanged)
     uint32_t leaf_threshold = 6, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
     bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
     int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (quantised when the scene extent allows) | 1 "q15" | 2 "f32"
@@ -145,10 +146,10 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         c->wf_batch = (uint32_t)n;
         return VCRT_OK;
     }
-    if (k == "leaf_threshold" || k == "shade_threshold") {
+    if (k == "leaf_threshold" || k == "shade_threshold" || k == "continue_threshold") {
         const int n = atoi(value);
         if (n < 1 || n > 32) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: threshold must be 1..32 lanes");
-        (k == "leaf_threshold" ? c->leaf_threshold : c->shade_threshold) = (uint32_t)n;
+        (k == "leaf_threshold" ? c->leaf_threshold : k == "shade_threshold" ? c->shade_threshold : c->continue_threshold) = (uint32_t)n;
         return VCRT_OK;
     }
     return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: unknown option '" + k + "'");
@@ -332,7 +333,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     a.target = (uchar4*)c->target.ptr; a.accum8 = (uchar4*)c->accum8.ptr; a.accumf = (float4*)c->accumf.ptr; a.aov = (vcrt_aov*)c->aov.ptr;
     a.counters = c->d_counters;
     a.work_counter = (unsigned int*)(c->d_counters + 3);
-    a.leaf_threshold = c->leaf_threshold; a.shade_threshold = c->shade_threshold;
+    a.leaf_threshold = c->leaf_threshold; a.shade_threshold = c->shade_threshold; a.continue_threshold = c->continue_threshold;
 
     cudaEvent_t e0, e1;
     CU(c, cudaEventCreate(&e0), "create event");

@@ -67,11 +67,21 @@ VCRT_HD float4 ldg4(const float4* p) {
 
 // One 256-bit read-only load (LDG.E.256 on sm_100a): a divergent lane costs one L1 data-pipe wavefront per 32-byte
 // sector it touches, so 32 bytes per instruction halves the wavefronts of two 128-bit loads.  p must be 32-byte aligned.
+#ifndef VCRT_L2HINT
+#define VCRT_L2HINT 1
+#endif
 struct __align__(32) Words8 { uint32_t w[8]; };
 VCRT_HD Words8 ldg8(const Words8* p) {
 #ifdef __CUDA_ARCH__
     Words8 r;
+    // VCRT_L2HINT: scene records are marked evict-last in L2 (LDG.E.ELL2.256) and the ray queues evict-first (stream_*
+    // below): a trace launch streams ~1 GB of queue records past a ~100 MB scene, and without the hints 27 % of the
+    // kernel's L2 sector requests went to DRAM (ncu r01_v8), i.e. most warp iterations waited on at least one DRAM miss.
+#if VCRT_L2HINT
+    asm("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
     return r;
 #else
@@ -80,6 +90,19 @@ VCRT_HD Words8 ldg8(const Words8* p) {
     return r;
 #endif
 }
+
+// Streaming accesses of the wavefront queues (read once / written once per bounce): evict-first when VCRT_L2HINT.
+#if defined(__CUDA_ARCH__) && VCRT_L2HINT
+__device__ __forceinline__ float4 stream_ld(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 stream_ld(const uint2* p) { return __ldcs(p); }
+__device__ __forceinline__ void stream_st(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void stream_st(uint2* p, uint2 v) { __stcs(p, v); }
+#else
+VCRT_HD float4 stream_ld(const float4* p) { return *p; }
+VCRT_HD uint2 stream_ld(const uint2* p) { return *p; }
+VCRT_HD void stream_st(float4* p, float4 v) { *p = v; }
+VCRT_HD void stream_st(uint2* p, uint2 v) { *p = v; }
+#endif
 
 // Hint: bring the line holding p into L1 (no register, no scoreboard wait).  No-op on the host.
 VCRT_HD void prefetch_l1(const void* p) {
@@ -99,7 +122,10 @@ VCRT_HD void prefetch_l1(const void* p) {
 #define VCRT_Q15_SEL_HI 0x7324u
 VCRT_HD float q15_sel(uint32_t w, uint32_t sel) {
 #ifdef __CUDA_ARCH__
-    return __uint_as_float(__byte_perm(w, 0x3F000000u, sel));
+    // prmt.b32 directly: __byte_perm would first mask the selector (one LOP3 per axis and visit)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x3F000000u), "r"(sel));
+    return __uint_as_float(r);
 #else
     return u2f(0x3F000000u | ((sel == VCRT_Q15_SEL_LO ? (w & 0xffffu) : (w >> 16)) << 8));
 #endif

@@ -16,8 +16,8 @@
 #ifndef VCRT_MEGA_MINB
 #define VCRT_MEGA_MINB 1  /* megakernel (A/B variant): it carries the shading state too, no register cap */
 #endif
-#ifndef VCRT_PEND_DEPTH
-#define VCRT_PEND_DEPTH 1  /* trace kernel: leaves a lane may postpone before it has to wait for the leaf phase */
+#ifndef VCRT_VISITS
+#define VCRT_VISITS 2  /* trace kernel: inner-node visits per lane between two warp votes on the phase switch */
 #endif
 #ifndef VCRT_PREFETCH
 #define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */

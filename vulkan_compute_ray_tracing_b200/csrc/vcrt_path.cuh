@@ -24,6 +24,7 @@ struct KernelArgs {
     unsigned long long* counters;        // [0] rays [1] nodes [2] triangles
     unsigned int* work_counter;          // persistent kernels: next work item
     uint32_t leaf_threshold, shade_threshold;   // persistent kernel phase thresholds (lanes)
+    uint32_t continue_threshold;                // trace kernel: lanes on inner nodes at or above which the phase votes are skipped
 };
 
 // Work item -> pixel.  Items enumerate the owned 32x32 tiles; inside a tile, 32 consecutive items form an

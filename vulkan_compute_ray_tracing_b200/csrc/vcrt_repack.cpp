@@ -74,7 +74,7 @@ bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle
             }
         }
     }
-    if (out.depth + 2 > 48) { err = "bvh: depth " + std::to_string(out.depth) + " exceeds the fast traversal stack (46)"; return false; }
+    if (out.depth + 3 > 48) { err = "bvh: depth " + std::to_string(out.depth) + " exceeds the fast traversal stack (45)"; return false; }
     return true;
 }
 
@@ -202,7 +202,7 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err) {
 #pragma omp parallel
 #pragma omp single
     sb.build(0, n, 0, 0, root);
-    if (sb.max_depth.load() + 2 > 48) { err = "sah rebuild: depth " + std::to_string(sb.max_depth.load()) + " exceeds the fast traversal stack"; return false; }
+    if (sb.max_depth.load() + 3 > 48) { err = "sah rebuild: depth " + std::to_string(sb.max_depth.load()) + " exceeds the fast traversal stack"; return false; }
     fb.nodes.swap(sb.nodes);
     fb.root = 0;
     fb.depth = sb.max_depth.load();

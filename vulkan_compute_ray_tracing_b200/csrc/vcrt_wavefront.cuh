@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
     const uint32_t count = PRIMARY ? b.npaths : w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
     if (!PRIMARY && blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(a.counters + 0, (unsigned long long)count);
-    const int leaf_t = (int)a.leaf_threshold, refill_t = (int)a.shade_threshold;
+    const int leaf_t = (int)a.leaf_threshold, refill_t = (int)a.shade_threshold, cont_t = (int)a.continue_threshold;
 
     uint32_t idx = 0xffffffffu;          // ray in flight (0xffffffff: none)
     bool done = false;                   // the queue is exhausted for this lane
@@ -84,10 +84,8 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
     TravState t;
     t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = EMPTY; t.sp = 0;
     t.selx = t.sely = t.selz = VCRT_Q15_SEL_LO;
-    int32_t pending = EMPTY;
-#if VCRT_PEND_DEPTH == 2
-    int32_t pending2 = EMPTY;
-#endif
+    int32_t pending = EMPTY;             // one postponed leaf
+    int32_t tos = EMPTY;                 // top of the traversal stack (vcrt_fast.cuh: trav_inner_step_lean)
     int32_t stack[VCRT_FAST_STACK];
     stack[0] = EMPTY;                    // sentinel: popping an exhausted stack yields EMPTY
     TraceStats st = {0u, 0u, 0u};
@@ -95,7 +93,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
     for (;;) {
         // ---- refill: lanes whose ray is finished store the result and take the next ray
         if (!done && t.node == EMPTY && pending == EMPTY) {
-            if (idx != 0xffffffffu) w.hit[idx] = make_uint2(f2u(t.closest), (uint32_t)t.best);
+            if (idx != 0xffffffffu) stream_st(w.hit + idx, make_uint2(f2u(t.closest), (uint32_t)t.best));
             idx = atomicAdd(w.counts + 2, 1u);   // ptxas aggregates this per warp (REDUX + one ATOMG)
             if (idx < count) {
                 bool valid = true;
@@ -105,11 +103,12 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                     wf_primary(a, x, y, k, cur, rng);
                     if (valid) st.rays++;
                 } else {
-                    const float4 o = __ldg(rays + 3 * (size_t)idx), d = __ldg(rays + 3 * (size_t)idx + 1);
+                    const float4 o = stream_ld(rays + 3 * (size_t)idx), d = stream_ld(rays + 3 * (size_t)idx + 1);
                     cur.o = xyz(o); cur.d = xyz(d);
                 }
                 trav_begin<QN>(t, s, cur);
                 t.sp = 1;
+                tos = EMPTY;
                 if (!valid) { t.node = EMPTY; idx = 0xffffffffu; }   // a path outside the covered extent: nothing to trace or record
             } else {
                 done = true;
@@ -119,59 +118,41 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
         if (__all_sync(FULL, done)) break;
 
         for (;;) {
-            // ---- one inner-node visit for every lane that has one
-            if (t.node >= 0) {
-                if (COUNT) st.nodes++;
-                trav_inner_step_lean<QN>(t, s, stack);
+            // ---- VCRT_VISITS inner-node visits for every lane that has one; a lane that arrives at a leaf postpones it
+            //      (one leaf) and keeps traversing
+#pragma unroll
+            for (int v = 0; v < VCRT_VISITS; ++v) {
+                if (t.node >= 0) {
+                    if (COUNT) st.nodes++;
+                    trav_inner_step_lean<QN>(t, s, tos, stack);
+                }
+                if ((uint32_t)t.node > 0x80000000u && pending == EMPTY) {   // a leaf (negative and not EMPTY), nothing postponed yet
+                    pending = t.node;
+                    trav_pop(t, tos, stack);
+                }
             }
-            // a lane that arrives at a leaf postpones it (up to VCRT_PEND_DEPTH leaves) and keeps traversing
-            bool at_leaf = (uint32_t)t.node > 0x80000000u;          // negative and not EMPTY
-#if VCRT_PEND_DEPTH == 2
-            if (at_leaf && pending2 == EMPTY) {
-                if (pending == EMPTY) pending = t.node; else pending2 = t.node;
-                t.node = stack[--t.sp];
-                at_leaf = (uint32_t)t.node > 0x80000000u;
-            }
-#else
-            if (at_leaf && pending == EMPTY) {
-                pending = t.node;
-                t.node = stack[--t.sp];
-                at_leaf = (uint32_t)t.node > 0x80000000u;
-            }
-#endif
+            // ---- phase switch.  Common case first, one vote: enough lanes still have an inner node -> go on.  Only below
+            //      that does the warp look at who is blocked on a second leaf (nb) and who wants a new ray (nf).
             const bool inner = t.node >= 0;
             const unsigned mi = __ballot_sync(FULL, inner);
-            const unsigned mb = __ballot_sync(FULL, !inner && pending != EMPTY);   // cannot go on without the leaf phase
-            const unsigned mf = __ballot_sync(FULL, !done && t.node == EMPTY && pending == EMPTY);
-            if (mb != 0u && (__popc(mb) >= leaf_t || mi == 0u)) {
+            if (__popc(mi) >= cont_t) continue;
+            const int nb = __popc(__ballot_sync(FULL, !inner && pending != EMPTY));   // cannot go on without the leaf phase
+            const int nf = __popc(__ballot_sync(FULL, !done && t.node == EMPTY && pending == EMPTY));
+            if (mi != 0u && nb < leaf_t && nf < refill_t) continue;
+            if (nb != 0 && (nb >= leaf_t || mi == 0u)) {
                 // ---- leaf phase: every lane with a postponed leaf tests it
                 if (pending != EMPTY) {
                     if (COUNT) st.tris++;
                     trav_leaf_test(t, s, cur, pending);
-#if VCRT_PEND_DEPTH == 2
-                    pending = pending2;
-                    pending2 = EMPTY;
-#else
                     pending = EMPTY;
-#endif
                 }
-#if VCRT_PEND_DEPTH == 2
-                if (__any_sync(FULL, pending != EMPTY)) {   // second postponed leaves
-                    if (pending != EMPTY) {
-                        if (COUNT) st.tris++;
-                        trav_leaf_test(t, s, cur, pending);
-                        pending = EMPTY;
-                    }
-                }
-#endif
-                if (at_leaf) {   // the leaf the lane was blocked on becomes the postponed one
+                if ((uint32_t)t.node > 0x80000000u) {   // the leaf the lane was blocked on becomes the postponed one
                     pending = t.node;
-                    t.node = stack[--t.sp];
+                    trav_pop(t, tos, stack);
                 }
                 continue;
             }
-            if (mf != 0u && (__popc(mf) >= refill_t || mi == 0u)) break;
-            if (mi == 0u) break;   // only done lanes left (mb == 0 and mf == 0 here)
+            break;   // enough lanes want a new ray (nf >= refill_t), or nothing but finished lanes is left
         }
     }
     flush_stats(a, st);   // st.rays is non-zero only for PRIMARY (queued rays are counted once per launch above)
@@ -200,13 +181,13 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ K
                 thr = f3(1.0f, 1.0f, 1.0f);
                 q0 = make_float4(0, 0, 0, u2f(path));
             } else {
-                q0 = rays[3 * (size_t)i]; q1 = rays[3 * (size_t)i + 1]; q2 = rays[3 * (size_t)i + 2];
+                q0 = stream_ld(rays + 3 * (size_t)i); q1 = stream_ld(rays + 3 * (size_t)i + 1); q2 = stream_ld(rays + 3 * (size_t)i + 2);
                 path = f2u(q0.w); rng = f2u(q1.w);
                 cur.o = xyz(q0); cur.d = xyz(q1);
                 thr = xyz(q2);
                 wf_path_pixel(a, b, path, x, y, k);
             }
-            const uint2 h = w.hit[i];
+            const uint2 h = stream_ld(w.hit + i);
             TravState t;
             t.closest = u2f(h.x); t.best = (int32_t)h.y;
             Hit rec;
@@ -234,12 +215,12 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ K
             } else {
                 thr = scale(thr, 0.0f);
             }
-            if (!cont) w.sample_color[path] = make_float4(thr.x, thr.y, thr.z, 1.0f);
+            if (!cont) stream_st(w.sample_color + path, make_float4(thr.x, thr.y, thr.z, 1.0f));
         }
         const uint32_t slot = wf_append_slot(w.counts + (b.cur ^ 1u), cont);
         if (cont) {
             float4* q = next + 3 * (size_t)slot;
-            q[0] = q0; q[1] = q1; q[2] = q2;
+            stream_st(q, q0); stream_st(q + 1, q1); stream_st(q + 2, q2);
         }
     }
 }
@@ -254,11 +235,11 @@ __global__ void __launch_bounds__(256) wf_accumulate_kernel(const __grid_constan
     const float4* c = w.sample_color + (size_t)it * a.sample_count;
     if (a.accum_mode == VCRT_ACCUM_F32) {
         float4 acc = a.accumf[pix];
-        for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = c[k]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += 1.0f; }
+        for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = stream_ld(c + k); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += 1.0f; }
         a.accumf[pix] = acc;
     } else {
         uchar4 px = a.accum8[pix];
-        for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = c[k]; running_mean_rgba8(px, f3(v.x, v.y, v.z), a.sample_begin + k); }
+        for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = stream_ld(c + k); running_mean_rgba8(px, f3(v.x, v.y, v.z), a.sample_begin + k); }
         a.target[pix] = px;
         a.accum8[pix] = px;
     }
