@@ -60,6 +60,8 @@ extern "C" int hostemu_render(const void* tris, uint32_t ntris, const void* mats
             s.qnodes = (const Words8*)fb.qnodes.data();   // std::vector storage is 16-byte aligned; the host load is a plain copy
             s.qorg = make_float3(fb.qorg[0], fb.qorg[1], fb.qorg[2]);
             s.qext = make_float3(fb.qext[0], fb.qext[1], fb.qext[2]);
+            // test hook: _reserved bit 3 walks the 4-wide form of the quantised tree
+            if ((p->_reserved & 8u) && build_wide_bvh(fb, VCRT_FAST_STACK)) { s.q4nodes = (const Words8*)fb.q4nodes.data(); s.froot4 = fb.root4; }
         }
     }
     const bool ref_cov = (p->flags & VCRT_FLAG_REF_DISPATCH_COVERAGE) != 0;

@@ -72,14 +72,15 @@ def test_repack_rejects_unsupported_trees(hostemu):
         hostemu.render(sc, (0.0, 6.0, 1.5), 32, 32, make_params(traversal="fast"))
 
 
-@pytest.mark.parametrize("fmt", ["auto", "f32", "q15_forced"])
+@pytest.mark.parametrize("fmt", ["auto", "f32", "q15_forced", "q15x4", "q15x4_forced"])
 def test_node_formats_give_identical_results(oracle, hostemu, doge, fmt):
     """32-byte quantised nodes (one 256-bit load per visit) vs 64-byte float nodes: boxes only cull, so every output
     bit is the same; the quantised tree may only visit MORE nodes.  `q15_forced` also runs a scene 1000x larger than the
-    quantiser's automatic limit (coarse quanta: correctness must not depend on them)."""
-    reserved = {"auto": 0, "f32": 2, "q15_forced": 4}[fmt]
+    quantiser's automatic limit (coarse quanta: correctness must not depend on them).  `q15x4` walks the 4-wide form of the
+    quantised tree (four children per visit, vcrt_repack.h: build_wide_bvh): same bits again, and far fewer visits."""
+    reserved = {"auto": 0, "f32": 2, "q15_forced": 4, "q15x4": 8, "q15x4_forced": 12}[fmt]
     cases = [(doge, CAM, 160, 120), (small_scene(n_tris=3000, seed=11), (0.0, 6.0, 1.5), 96, 64)]
-    if fmt == "q15_forced":
+    if fmt.endswith("_forced"):
         big = small_scene(n_tris=800, seed=12)
         big = dict(big)
         t = big["triangles"].copy().view(np.float32).reshape(-1, 12)
@@ -98,6 +99,10 @@ def test_node_formats_give_identical_results(oracle, hostemu, doge, fmt):
         pf = make_params(traversal="fast", **kw)
         pf._reserved = 2
         f = hostemu.render(sc, cam, w, h, pf, want_aov=True)
-        assert b["nodes"] >= f["nodes"] and b["rays"] == f["rays"]
+        assert b["rays"] == f["rays"]
+        if fmt.startswith("q15x4"):
+            assert b["nodes"] < 0.75 * f["nodes"]          # a 4-wide visit replaces about two binary ones
+            continue
+        assert b["nodes"] >= f["nodes"]
         if fmt != "f32" and sc is doge:
             assert b["nodes"] <= 1.1 * f["nodes"]        # quantisation costs only a few per cent more visits here

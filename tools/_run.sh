@@ -1,4 +1,3 @@
-mkdir -p gpurun_out/v11
-python -m pytest tests -m gpu -x -q > gpurun_out/v11/pytest.log 2>&1; tail -3 gpurun_out/v11/pytest.log
-bash tools/ab_libs.sh "lib lib_nohint" --spp 16 --trace 2>&1 | tee gpurun_out/v11/ab.log
-bash tools/ab_libs.sh "lib lib_nohint" --spp 64 --trace 2>&1 | tee -a gpurun_out/v11/ab.log
+mkdir -p gpurun_out/v15
+bash tools/ab_libs.sh "lib_w1 lib_w1p9 lib_w1p8 lib_w1r lib_w1r12" --spp 32 --trace 2>&1 | tee gpurun_out/v15/ab.log
+VCRT_LIB=$PWD/vulkan_compute_ray_tracing_b200/lib_w1/libvcrt.so python tools/sweep.py --spp 32 --trace leaf_threshold=4,6,8,12 shade_threshold=4,8,12 continue_threshold=20,26 2>&1 | tee gpurun_out/v15/sweep.log

@@ -34,8 +34,11 @@ struct vcrt_ctx {
     uint32_t continue_threshold = 20;   // option "continue_threshold" (33 - min(leaf, shade) leaves the schedule unchanged)
     uint32_t leaf_threshold = 6, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
     bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
-    int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (quantised when the scene extent allows) | 1 "q15" | 2 "f32"
-    bool quantized = false;
+    int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (4-wide quantised when the scene extent allows) | 1 "q15" (binary) | 2 "f32" | 3 "q15x4"
+    bool quantized = false, wide = false;
+    int32_t froot4 = (int32_t)0x80000000;
+    uint32_t nf4nodes = 0;
+    DevBuf q4nodes;
     float qorg[3] = {0, 0, 0}, qext[3] = {0, 0, 0};
     DevBuf qnodes;
     uint32_t fast_depth = 0;
@@ -129,8 +132,8 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         return VCRT_OK;
     }
     if (k == "fast_nodes") {
-        const int m = v == "auto" ? 0 : v == "q15" ? 1 : v == "f32" ? 2 : -1;
-        if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: fast_nodes must be 'auto', 'q15' or 'f32'");
+        const int m = v == "auto" ? 0 : v == "q15" ? 1 : v == "f32" ? 2 : v == "q15x4" ? 3 : -1;
+        if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: fast_nodes must be 'auto', 'q15x4', 'q15' or 'f32'");
         if (m != c->fast_nodes) { c->fast_nodes = m; c->fast_dirty = true; }
         return VCRT_OK;
     }
@@ -164,8 +167,8 @@ int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
     if (k == "fast_nodes" || k == "fast_node_count" || k == "fast_depth") {
         CU(c, cudaSetDevice(c->device), "set device");
         const bool ok = prepare_fast(c) == VCRT_OK;
-        if (k == "fast_nodes") v = !ok ? "none" : c->quantized ? "q15" : "f32";
-        else if (k == "fast_node_count") v = std::to_string(ok ? c->nfnodes : 0u);
+        if (k == "fast_nodes") v = !ok ? "none" : c->wide ? "q15x4" : c->quantized ? "q15" : "f32";
+        else if (k == "fast_node_count") v = std::to_string(ok ? (c->wide ? c->nf4nodes : c->nfnodes) : 0u);
         else v = std::to_string(ok ? c->fast_depth : 0u);
     } else if (k == "wf_batch_paths") v = std::to_string(c->wf_batch);
     else if (k == "device") v = std::to_string(c->device);
@@ -190,7 +193,7 @@ int vcrt_destroy(vcrt_ctx* c) {
     for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c->trace_timer.destroy();
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
-    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes, &c->present}) if (b->ptr) cudaFree(b->ptr);
+    for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes, &c->q4nodes, &c->present}) if (b->ptr) cudaFree(b->ptr);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -282,7 +285,15 @@ static int prepare_fast(vcrt_ctx* c) {
             if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
             if (!fb.tris64.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris64.data(), fb.tris64.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
             // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
-            c->quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, c->fast_nodes == 1 ? 3.0e38f : 2.5e-4f);
+            c->quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, (c->fast_nodes == 1 || c->fast_nodes == 3) ? 3.0e38f : 2.5e-4f);
+            // 4-wide form of the quantised tree for the wavefront trace kernel ("auto" and "q15x4"; "q15" keeps the binary tree)
+            c->wide = c->quantized && c->fast_nodes != 1 && build_wide_bvh(fb, VCRT_FAST_STACK);
+            if (c->wide) {
+                if ((rc = ensure(c, c->q4nodes, fb.q4nodes.size() * 4, "allocate 4-wide nodes"))) return rc;
+                CU(c, cudaMemcpyAsync(c->q4nodes.ptr, fb.q4nodes.data(), fb.q4nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload 4-wide nodes");
+                c->froot4 = fb.root4;
+                c->nf4nodes = (uint32_t)(fb.q4nodes.size() / 16);
+            }
             if (c->quantized) {
                 if ((rc = ensure(c, c->qnodes, fb.qnodes.size() * 4, "allocate quantised nodes"))) return rc;
                 CU(c, cudaMemcpyAsync(c->qnodes.ptr, fb.qnodes.data(), fb.qnodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload quantised nodes");
@@ -325,6 +336,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
             s.qorg = make_float3(c->qorg[0], c->qorg[1], c->qorg[2]);
             s.qext = make_float3(c->qext[0], c->qext[1], c->qext[2]);
         }
+        if (c->wide) { s.q4nodes = (const Words8*)c->q4nodes.ptr; s.froot4 = c->froot4; }
     } else {
         s.froot = (int32_t)0x80000000;
     }

@@ -249,6 +249,8 @@ struct SceneView {
     int32_t froot;          // >= 0 inner node, < 0 leaf (~triangle slot), INT_MIN empty
     // 32-byte quantised inner nodes (vcrt_repack.h: quantize_fast_bvh); null = walk the 64-byte float nodes
     const Words8* qnodes;
+    const Words8* q4nodes;  // 4-wide quantised nodes (two Words8 per node) or null; root = froot4
+    int32_t froot4;
     float3 qorg, qext;      // coordinate = qorg + 2m * qext
 };
 

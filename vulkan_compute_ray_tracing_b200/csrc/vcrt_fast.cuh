@@ -22,10 +22,11 @@
 #pragma once
 
 #include "vcrt_core.cuh"
+#include "vcrt_tunables.h"
 
 namespace vcrt {
 
-#define VCRT_FAST_STACK 48
+#define VCRT_FAST_STACK 64
 #define VCRT_FAST_EMPTY ((int32_t)0x80000000)
 
 VCRT_HD float fmin_(float a, float b) { return fminf(a, b); }
@@ -61,30 +62,33 @@ VCRT_HD void trav_begin(TravState& t, const SceneView& s, const Ray& r) {
     }
     t.closest = VCRT_T_MAX;
     t.best = -1;
-    t.node = s.froot;
+    t.node = QN == 2 ? s.froot4 : s.froot;
     t.sp = 0;
 }
 
+// The two children of a quantised 32-byte node (already in registers) against the ray: near/far planes are picked by the
+// direction sign at decode time, so the slab test needs no per-axis min/max.
+VCRT_HD void trav_test_children_q(const TravState& t, const Words8& n, float& lN, float& rN, bool& hl, bool& hr, int32_t& cl, int32_t& cr) {
+    const uint32_t fx = t.selx ^ 0x0220u, fy = t.sely ^ 0x0220u, fz = t.selz ^ 0x0220u;
+    const float lnx = fmaf(q15_sel(n.w[0], t.selx), t.idir.x, -t.ood.x), lfx = fmaf(q15_sel(n.w[0], fx), t.idir.x, -t.ood.x);
+    const float lny = fmaf(q15_sel(n.w[1], t.sely), t.idir.y, -t.ood.y), lfy = fmaf(q15_sel(n.w[1], fy), t.idir.y, -t.ood.y);
+    const float lnz = fmaf(q15_sel(n.w[2], t.selz), t.idir.z, -t.ood.z), lfz = fmaf(q15_sel(n.w[2], fz), t.idir.z, -t.ood.z);
+    const float rnx = fmaf(q15_sel(n.w[3], t.selx), t.idir.x, -t.ood.x), rfx = fmaf(q15_sel(n.w[3], fx), t.idir.x, -t.ood.x);
+    const float rny = fmaf(q15_sel(n.w[4], t.sely), t.idir.y, -t.ood.y), rfy = fmaf(q15_sel(n.w[4], fy), t.idir.y, -t.ood.y);
+    const float rnz = fmaf(q15_sel(n.w[5], t.selz), t.idir.z, -t.ood.z), rfz = fmaf(q15_sel(n.w[5], fz), t.idir.z, -t.ood.z);
+    cl = (int32_t)n.w[6]; cr = (int32_t)n.w[7];
+    lN = fmax_(fmax_(lnx, lny), fmax_(lnz, 0.0f));
+    rN = fmax_(fmax_(rnx, rny), fmax_(rnz, 0.0f));
+    const float lF = fmin_(fmin_(lfx, lfy), lfz) * 1.0000004f;
+    const float rF = fmin_(fmin_(rfx, rfy), rfz) * 1.0000004f;
+    hl = lN <= fmin_(lF, t.closest);
+    hr = rN <= fmin_(rF, t.closest);
+}
 // Both children of inner node t.node against the ray: entry distances (clamped to 0), hit verdicts and child codes.
 template <int QN>
 VCRT_HD void trav_test_children(const TravState& t, const SceneView& s, float& lN, float& rN, bool& hl, bool& hr, int32_t& cl, int32_t& cr) {
     if (QN) {
-        // near/far planes picked by the direction sign at decode time: no per-axis min/max
-        const Words8 n = ldg8(s.qnodes + t.node);
-        const uint32_t fx = t.selx ^ 0x0220u, fy = t.sely ^ 0x0220u, fz = t.selz ^ 0x0220u;
-        const float lnx = fmaf(q15_sel(n.w[0], t.selx), t.idir.x, -t.ood.x), lfx = fmaf(q15_sel(n.w[0], fx), t.idir.x, -t.ood.x);
-        const float lny = fmaf(q15_sel(n.w[1], t.sely), t.idir.y, -t.ood.y), lfy = fmaf(q15_sel(n.w[1], fy), t.idir.y, -t.ood.y);
-        const float lnz = fmaf(q15_sel(n.w[2], t.selz), t.idir.z, -t.ood.z), lfz = fmaf(q15_sel(n.w[2], fz), t.idir.z, -t.ood.z);
-        const float rnx = fmaf(q15_sel(n.w[3], t.selx), t.idir.x, -t.ood.x), rfx = fmaf(q15_sel(n.w[3], fx), t.idir.x, -t.ood.x);
-        const float rny = fmaf(q15_sel(n.w[4], t.sely), t.idir.y, -t.ood.y), rfy = fmaf(q15_sel(n.w[4], fy), t.idir.y, -t.ood.y);
-        const float rnz = fmaf(q15_sel(n.w[5], t.selz), t.idir.z, -t.ood.z), rfz = fmaf(q15_sel(n.w[5], fz), t.idir.z, -t.ood.z);
-        cl = (int32_t)n.w[6]; cr = (int32_t)n.w[7];
-        lN = fmax_(fmax_(lnx, lny), fmax_(lnz, 0.0f));
-        rN = fmax_(fmax_(rnx, rny), fmax_(rnz, 0.0f));
-        const float lF = fmin_(fmin_(lfx, lfy), lfz) * 1.0000004f;
-        const float rF = fmin_(fmin_(rfx, rfy), rfz) * 1.0000004f;
-        hl = lN <= fmin_(lF, t.closest);
-        hr = rN <= fmin_(rF, t.closest);
+        trav_test_children_q(t, ldg8(s.qnodes + t.node), lN, rN, hl, hr, cl, cr);
         return;
     }
     float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
@@ -107,6 +111,36 @@ VCRT_HD void trav_test_children(const TravState& t, const SceneView& s, float& l
     hr = rN <= fmin_(rF, t.closest);
 }
 
+// ---- 4-wide nodes (vcrt_repack.h: build_wide_bvh): a node is two halves in the quantised binary format.
+// Tests the four children and returns them ordered by entry distance: c[0] the nearest hit child ... ; children that are
+// missed (or absent) come last with code VCRT_FAST_EMPTY.  Any order is correct (ties are decided by slot rank); nearest
+// first makes t-culling effective.
+VCRT_HD void trav_test4(const TravState& t, const Words8& a, const Words8& b, int32_t c[4]) {
+    float d[4];
+    bool h[4];
+    trav_test_children_q(t, a, d[0], d[1], h[0], h[1], c[0], c[1]);
+    trav_test_children_q(t, b, d[2], d[3], h[2], h[3], c[2], c[3]);
+    const float inf = u2f(0x7f800000u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { d[i] = h[i] ? d[i] : inf; c[i] = h[i] ? c[i] : VCRT_FAST_EMPTY; }
+    // 5-comparator network; strict compare, so absent children (inf) never move in front of anything
+#define VCRT_CSWAP(i, j) { const bool sw = d[j] < d[i]; const float dl = sw ? d[j] : d[i], dh = sw ? d[i] : d[j]; const int32_t cl_ = sw ? c[j] : c[i], ch_ = sw ? c[i] : c[j]; d[i] = dl; d[j] = dh; c[i] = cl_; c[j] = ch_; }
+    VCRT_CSWAP(0, 1) VCRT_CSWAP(2, 3) VCRT_CSWAP(0, 2) VCRT_CSWAP(1, 3) VCRT_CSWAP(1, 2)
+#undef VCRT_CSWAP
+}
+
+// Visit 4-wide inner node t.node (generic form: plain stack; the static kernels and the host emulation).
+VCRT_HD void trav_inner_step4(TravState& t, const SceneView& s, int32_t* stack) {
+    const Words8* p = s.q4nodes + 2 * (size_t)t.node;
+    const Words8 a = ldg8(p), b = ldg8(p + 1);
+    int32_t c[4];
+    trav_test4(t, a, b, c);
+    if (c[0] == VCRT_FAST_EMPTY) { t.node = t.sp ? stack[--t.sp] : VCRT_FAST_EMPTY; return; }
+    t.node = c[0];
+    for (int i = 3; i >= 1; --i)
+        if (c[i] != VCRT_FAST_EMPTY && t.sp < VCRT_FAST_STACK) stack[t.sp++] = c[i];
+}
+
 // Visit inner node t.node: test both children, descend into the nearer hit child, push the farther one.
 template <int QN>
 VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
@@ -127,29 +161,95 @@ VCRT_HD void trav_inner_step(TravState& t, const SceneView& s, int32_t* stack) {
     }
 }
 
-// The same visit for the wavefront trace kernel, written for predication instead of branches, with the top of the stack
-// held in a register (`tos`): a pop takes its node from the register and issues the load of the next entry, whose
-// latency is then off the critical path (ncu r01_v8: 18 % of the stall samples of the memory-stack version sat on the
-// instruction that consumes the popped entry).  stack[0] holds the sentinel VCRT_FAST_EMPTY and t.sp starts at 1 with
-// tos = EMPTY, so pops are unconditional and an exhausted stack yields EMPTY without a test; depth never exceeds the stack
-// (vcrt_repack.cpp rejects deeper trees), so "push" needs no bound check.
-VCRT_HD void trav_pop(TravState& t, int32_t& tos, const int32_t* stack) {
-    t.node = tos;
-    tos = stack[--t.sp];
+// The same visit for the wavefront trace kernel (device only), written for predication instead of branches, with the top
+// of the stack held in a register (`tos`): a pop takes its node from the register and issues the load of the next entry,
+// whose latency is then off the critical path.  stack[0] holds the sentinel VCRT_FAST_EMPTY and t.sp starts at 1 with
+// tos = EMPTY, so an exhausted stack yields EMPTY without a test; depth never exceeds the stack (vcrt_repack.cpp rejects
+// deeper trees), so "push" needs no bound check.
+// The stack accesses are predicated ld.local / st.local written in PTX with the load's destination tied to `tos`: left to
+// itself the compiler loads the popped entry into a temporary and moves it into the tos register right away, and that
+// move waits out the whole load (ncu r01_v9: 16 % of the trace kernel's stall samples sat on those moves).  `sbase` is
+// the local-window byte address of stack[0] (__cvta_generic_to_local).
+#ifdef __CUDACC__
+__device__ __forceinline__ void stk_load_if(bool p, int32_t& dst, uint32_t addr) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.local.b32 %0, [%1];\n\t}" : "+r"(dst) : "r"(addr), "r"((uint32_t)p) : "memory");
 }
-template <int QN>
-VCRT_HD void trav_inner_step_lean(TravState& t, const SceneView& s, int32_t& tos, int32_t* stack) {
-    float lN, rN;
-    bool hl, hr;
-    int32_t cl, cr;
-    trav_test_children<QN>(t, s, lN, rN, hl, hr, cl, cr);
+__device__ __forceinline__ void stk_store_if(bool p, uint32_t addr, int32_t v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.local.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void stk_lds_if(bool p, int32_t& dst, uint32_t addr) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.b32 %0, [%1];\n\t}" : "+r"(dst) : "r"(addr), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void stk_sts_if(bool p, uint32_t addr, int32_t v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+// Where the entries below the register-held top live.  The first VCRT_SSTACK slots of every lane are in shared memory,
+// laid out [slot][thread]: whatever the lanes' depths, a warp's access touches 32 different banks = one wavefront, where
+// the same access to local memory costs one L1 sector per distinct depth among the lanes (ncu r01_v9: 3.2 sectors per
+// request, and stack traffic was 37 % of all L1 sectors of the kernel).  Deeper slots fall back to local memory.
+struct StackRef {
+    uint32_t lbase;   // local-window byte address of the local part
+    uint32_t sbase;   // shared-window byte address of this thread's slot 0
+    __device__ __forceinline__ void store_if(bool p, int sp, int32_t v) const {
+#if VCRT_SSTACK
+        const bool sh = sp < VCRT_SSTACK;
+        stk_sts_if(p && sh, sbase + (uint32_t)sp * (4u * VCRT_PBLOCK), v);
+        stk_store_if(p && !sh, lbase + 4u * (uint32_t)(sp - VCRT_SSTACK), v);
+#else
+        stk_store_if(p, lbase + 4u * (uint32_t)sp, v);
+#endif
+    }
+    __device__ __forceinline__ void load_if(bool p, int sp, int32_t& dst) const {
+#if VCRT_SSTACK
+        const bool sh = sp < VCRT_SSTACK;
+        stk_lds_if(p && sh, dst, sbase + (uint32_t)sp * (4u * VCRT_PBLOCK));
+        stk_load_if(p && !sh, dst, lbase + 4u * (uint32_t)(sp - VCRT_SSTACK));
+#else
+        stk_load_if(p, dst, lbase + 4u * (uint32_t)sp);
+#endif
+    }
+};
+// node = tos; tos = stack[--sp], for the lanes where p holds
+__device__ __forceinline__ void trav_pop_if(bool p, TravState& t, int32_t& tos, const StackRef& sr) {
+    t.node = p ? tos : t.node;
+    t.sp -= (int)p;
+    sr.load_if(p, t.sp, tos);
+}
+// The stack side of a visit, given the verdicts on the two children.  The near child, when it is a leaf and nothing is
+// parked yet, goes straight into `pending` and the lane goes on with the far child (or with the stack): no push + pop
+// round trip through local memory for it.
+__device__ __forceinline__ void trav_descend(TravState& t, float lN, float rN, bool hl, bool hr, int32_t cl, int32_t cr, int32_t& pending, int32_t& tos, const StackRef& sr) {
     const bool left_first = hl & (!hr | (lN <= rN));   // bitwise on purpose: one predicate LUT instead of materialised booleans
     const int32_t near_c = left_first ? cl : cr, far_c = left_first ? cr : cl;
     const bool both = hl && hr, none = !(hl || hr);
-    if (both) { stack[t.sp++] = tos; tos = far_c; }
-    t.node = near_c;
-    if (none) trav_pop(t, tos, stack);
+    const bool park = !none && near_c < 0 && pending == VCRT_FAST_EMPTY;
+    pending = park ? near_c : pending;
+    const bool push = both && !park, pop = none || (park && !both);
+    sr.store_if(push, t.sp, tos);   // push: the old top goes to memory, the far child becomes the top
+    t.sp += (int)push;
+    t.node = pop ? tos : (park ? far_c : near_c);
+    tos = push ? far_c : tos;
+    t.sp -= (int)pop;                                        // pop: the top becomes the node, the next entry is loaded into tos
+    sr.load_if(pop, t.sp, tos);
 }
+// The stack side of a 4-wide visit.  c[] as returned by trav_test4.  The nearest child, when it is a leaf and nothing is
+// parked yet, goes into `pending`; of the remaining k children the nearest becomes the node, the others go onto the stack
+// farthest first (the old top moves to memory, the second nearest becomes the new top).
+__device__ __forceinline__ void trav_descend4(TravState& t, int32_t c[4], int32_t& pending, int32_t& tos, const StackRef& sr) {
+    const bool park = c[0] != VCRT_FAST_EMPTY && c[0] < 0 && pending == VCRT_FAST_EMPTY;
+    pending = park ? c[0] : pending;
+    c[0] = park ? c[1] : c[0]; c[1] = park ? c[2] : c[1]; c[2] = park ? c[3] : c[2]; c[3] = park ? VCRT_FAST_EMPTY : c[3];
+    const bool k1 = c[0] != VCRT_FAST_EMPTY, k2 = c[1] != VCRT_FAST_EMPTY, k3 = c[2] != VCRT_FAST_EMPTY, k4 = c[3] != VCRT_FAST_EMPTY;
+    sr.store_if(k2, t.sp, tos);
+    sr.store_if(k3, t.sp + 1, k4 ? c[3] : c[2]);
+    sr.store_if(k4, t.sp + 2, c[2]);
+    t.sp += (int)k2 + (int)k3 + (int)k4;
+    t.node = k1 ? c[0] : tos;
+    tos = k2 ? c[1] : tos;
+    t.sp -= (int)!k1;                                        // nothing left here: pop
+    sr.load_if(!k1, t.sp, tos);
+}
+#endif
 
 // Test the triangle of leaf code `leaf` (= ~slot) with the reference's arithmetic and tie rule.
 VCRT_HD void trav_leaf_test(TravState& t, const SceneView& s, const Ray& r, int32_t leaf) {
@@ -181,7 +281,8 @@ VCRT_HD bool hit_bvh_fast_q(const SceneView& s, const Ray& r, Hit& rec, TraceSta
     while (t.node != VCRT_FAST_EMPTY) {
         if (t.node >= 0) {
             if (COUNT) st.nodes++;
-            trav_inner_step<QN>(t, s, stack);
+            if (QN == 2) trav_inner_step4(t, s, stack);
+            else trav_inner_step<QN>(t, s, stack);
         } else {
             if (COUNT) st.tris++;
             trav_leaf_test(t, s, r, t.node);
@@ -193,6 +294,7 @@ VCRT_HD bool hit_bvh_fast_q(const SceneView& s, const Ray& r, Hit& rec, TraceSta
 
 template <bool COUNT>
 VCRT_HD bool hit_bvh_fast(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
+    if (s.q4nodes) return hit_bvh_fast_q<COUNT, 2>(s, r, rec, st);
     return s.qnodes ? hit_bvh_fast_q<COUNT, 1>(s, r, rec, st) : hit_bvh_fast_q<COUNT, 0>(s, r, rec, st);
 }
 

@@ -104,21 +104,22 @@ template <int SHADER, int RNG_MODE, int TRIG>
 static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
     // the trace variants: [COUNT][QN][PRIMARY]
     typedef void (*TraceFn)(const KernelArgs, const WfQueues, const WfBatch);
-    static const TraceFn trace_fn[2][2][2] = {{{wf_trace_kernel<false, 0, false>, wf_trace_kernel<false, 0, true>}, {wf_trace_kernel<false, 1, false>, wf_trace_kernel<false, 1, true>}},
-                                              {{wf_trace_kernel<true, 0, false>, wf_trace_kernel<true, 0, true>}, {wf_trace_kernel<true, 1, false>, wf_trace_kernel<true, 1, true>}}};
-    static int trace_grid[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}}, sms = 0;
+    static const TraceFn trace_fn[2][3][2] = {
+        {{wf_trace_kernel<false, 0, false>, wf_trace_kernel<false, 0, true>}, {wf_trace_kernel<false, 1, false>, wf_trace_kernel<false, 1, true>}, {wf_trace_kernel<false, 2, false>, wf_trace_kernel<false, 2, true>}},
+        {{wf_trace_kernel<true, 0, false>, wf_trace_kernel<true, 0, true>}, {wf_trace_kernel<true, 1, false>, wf_trace_kernel<true, 1, true>}, {wf_trace_kernel<true, 2, false>, wf_trace_kernel<true, 2, true>}}};
+    static int trace_grid[2][3][2] = {{{0, 0}, {0, 0}, {0, 0}}, {{0, 0}, {0, 0}, {0, 0}}}, sms = 0;
     if (sms == 0) {
         int dev = 0, per_sm = 0;
         cudaError_t e;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         for (int c = 0; c < 2; ++c)
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 3; ++q)
                 for (int p = 0; p < 2; ++p) {
                     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_fn[c][q][p], VCRT_PBLOCK, 0)) != cudaSuccess) return e;
                     trace_grid[c][q][p] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: one resident wave
                 }
     }
-    const int ci = count ? 1 : 0, qi = a.scene.qnodes ? 1 : 0;
+    const int ci = count ? 1 : 0, qi = a.scene.q4nodes ? 2 : a.scene.qnodes ? 1 : 0;
     const uint32_t items = a.owned_tiles * 1024u;
     const uint32_t per_batch = w.capacity / a.sample_count;   // capacity >= sample_count is guaranteed by the caller
     const uint32_t shade_grid = (uint32_t)sms * 8u;

@@ -5,23 +5,7 @@
 #include <vector>
 #include "vcrt_path.cuh"
 
-#define VCRT_BLOCK 128
-#ifndef VCRT_PBLOCK
-#define VCRT_PBLOCK 128   /* persistent kernel: threads per block */
-#endif
-#ifndef VCRT_PMINB
-#define VCRT_PMINB 10    /* persistent kernels: min resident blocks per SM = register cap 48 (r01 A/B on C3: 1 -> 4328, 9 -> 4487, 10 -> 4586, 12 -> 4516 Mrays/s) */
-#endif
-
-#ifndef VCRT_MEGA_MINB
-#define VCRT_MEGA_MINB 1  /* megakernel (A/B variant): it carries the shading state too, no register cap */
-#endif
-#ifndef VCRT_VISITS
-#define VCRT_VISITS 2  /* trace kernel: inner-node visits per lane between two warp votes on the phase switch */
-#endif
-#ifndef VCRT_PREFETCH
-#define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
-#endif
+#include "vcrt_tunables.h"
 
 namespace vcrt {
 struct WfQueues;

@@ -231,6 +231,22 @@ void precompute_triangles(FastBvh& fb) {
 void set_repack_threads(int n) { omp_set_num_threads(n < 1 ? 1 : n); }
 
 // ------------------------------------------------------------------------------------------ quantisation
+namespace {
+// One axis of one box in the frame (qorg, qext): {lo | hi << 16}, rounded outwards; the empty box (min > max) for mn > mx.
+inline uint32_t quant_bounds(const FastBvh& fb, int a, double mn, double mx) {
+    uint32_t qlo = 32767u, qhi = 0u;         // empty child: min > max on every axis, never entered
+    if (mn <= mx) {
+        // decoded value = qorg + (1 + q/32768) * qext, evaluated with the floats the kernel uses
+        const double org = fb.qorg[a], ext = fb.qext[a];
+        double l = std::floor((mn - org - ext) / ext * 32768.0), h = std::ceil((mx - org - ext) / ext * 32768.0);
+        while (l > 0.0 && org + (1.0 + l / 32768.0) * ext > mn) l -= 1.0;
+        while (h < 32767.0 && org + (1.0 + h / 32768.0) * ext < mx) h += 1.0;
+        qlo = (uint32_t)std::min(std::max(l, 0.0), 32767.0);
+        qhi = (uint32_t)std::min(std::max(h, 0.0), 32767.0);
+    }
+    return qlo | (qhi << 16);
+}
+}  // namespace
 bool quantize_fast_bvh(FastBvh& fb, float max_quantum) {
     fb.qnodes.clear();
     const uint32_t n = fb.num_nodes();
@@ -273,21 +289,86 @@ bool quantize_fast_bvh(FastBvh& fb, float max_quantum) {
         for (int c = 0; c < 2; ++c)
             for (int a = 0; a < 3; ++a) {
                 const double mn = p[kMin[c][a]], mx = p[kMin[c][a] + 1];
-                uint32_t qlo = 32767u, qhi = 0u;         // empty child: min > max on every axis, never entered
-                if (mn <= mx) {
-                    // decoded value = qorg + (1 + q/32768) * qext, evaluated with the floats the kernel uses
-                    const double org = fb.qorg[a], ext = fb.qext[a];
-                    double l = std::floor((mn - org - ext) / ext * 32768.0), h = std::ceil((mx - org - ext) / ext * 32768.0);
-                    while (l > 0.0 && org + (1.0 + l / 32768.0) * ext > mn) l -= 1.0;
-                    while (h < 32767.0 && org + (1.0 + h / 32768.0) * ext < mx) h += 1.0;
-                    qlo = (uint32_t)std::min(std::max(l, 0.0), 32767.0);
-                    qhi = (uint32_t)std::min(std::max(h, 0.0), 32767.0);
-                }
-                q[c * 3 + a] = qlo | (qhi << 16);
+                const uint32_t word = quant_bounds(fb, a, mn, mx);
+                q[c * 3 + a] = word;
             }
         std::memcpy(&q[6], &p[12], 4);
         std::memcpy(&q[7], &p[13], 4);
     }
+    return true;
+}
+
+
+// ------------------------------------------------------------------------------------------ 4-wide tree
+bool build_wide_bvh(FastBvh& fb, uint32_t max_stack) {
+    fb.q4nodes.clear();
+    fb.root4 = fb.root;
+    fb.stack4 = 0;
+    if (fb.qnodes.empty() || fb.root < 0) return false;   // not quantised, or the tree is a single leaf / empty: the binary form serves
+    static const int kMin[2][3] = {{0, 2, 8}, {4, 6, 10}};
+    const int32_t EMPTY = (int32_t)0x80000000;
+    struct Child { float lo[3], hi[3]; int32_t code; };
+    auto children_of = [&](int32_t node, Child* out) {   // the (up to two) non-empty children of binary node `node`
+        const float* p = &fb.nodes[(size_t)node * 16];
+        int n = 0;
+        for (int c = 0; c < 2; ++c) {
+            int32_t code; std::memcpy(&code, &p[12 + c], 4);
+            if (code == EMPTY) continue;
+            Child& ch = out[n++];
+            for (int a = 0; a < 3; ++a) { ch.lo[a] = p[kMin[c][a]]; ch.hi[a] = p[kMin[c][a] + 1]; }
+            ch.code = code;
+        }
+        return n;
+    };
+    auto area = [](const Child& c) { const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2]; return dx * dy + dy * dz + dz * dx; };
+    struct Task { int32_t node2; uint32_t node4; uint32_t stack_above; };   // stack_above: entries already on the stack when this node is visited
+    std::vector<Task> todo;
+    std::vector<uint32_t>& out = fb.q4nodes;
+    out.reserve((size_t)fb.num_nodes() / 2 * 16 + 16);
+    out.resize(16);
+    todo.push_back({fb.root, 0u, 0u});
+    uint32_t need = 0;
+    while (!todo.empty()) {
+        const Task tk = todo.back();
+        todo.pop_back();
+        Child ch[4];
+        int n = children_of(tk.node2, ch);
+        while (n < 4) {   // open the inner child with the largest surface area
+            int best = -1; float ba = -1.0f;
+            for (int i = 0; i < n; ++i) if (ch[i].code >= 0 && area(ch[i]) > ba) { ba = area(ch[i]); best = i; }
+            if (best < 0) break;
+            Child sub[2];
+            const int m = children_of(ch[best].code, sub);
+            if (m == 0) { ch[best] = ch[--n]; continue; }      // cannot happen for trees built here (inner nodes have children)
+            ch[best] = sub[0];
+            if (m == 2) ch[n++] = sub[1];
+        }
+        // a visit leaves at most n - 1 entries behind and descends into one child
+        const uint32_t below = tk.stack_above + (n > 0 ? (uint32_t)(n - 1) : 0u);
+        if (below > need) need = below;
+        uint32_t w[16];
+        for (int i = 0; i < 4; ++i) {
+            uint32_t* half = w + (i / 2) * 8;
+            const int k = i & 1;
+            int32_t code = EMPTY;
+            for (int a = 0; a < 3; ++a) half[k * 3 + a] = 32767u;   // the empty box
+            if (i < n) {
+                for (int a = 0; a < 3; ++a) half[k * 3 + a] = quant_bounds(fb, a, ch[i].lo[a], ch[i].hi[a]);
+                code = ch[i].code;
+                if (code >= 0) {
+                    const uint32_t idx = (uint32_t)(out.size() / 16);
+                    out.resize(out.size() + 16);
+                    todo.push_back({code, idx, below});
+                    code = (int32_t)idx;
+                }
+            }
+            std::memcpy(&half[6 + k], &code, 4);
+        }
+        std::memcpy(&out[(size_t)tk.node4 * 16], w, sizeof w);
+    }
+    fb.stack4 = need + 2;   // + the sentinel slot and the register-held top's spill slot
+    if (fb.stack4 > max_stack) { fb.q4nodes.clear(); return false; }
+    fb.root4 = 0;
     return true;
 }
 

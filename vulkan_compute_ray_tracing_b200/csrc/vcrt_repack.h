@@ -12,6 +12,9 @@ struct FastBvh {
     std::vector<float> tris;       // 12 floats per triangle slot: {v0, original index} {v1, materialIndex} {v2, -}
     std::vector<float> tris64;     // 16 floats per slot, what the kernels read (precompute_triangles): {v0, index} {a, material} {b, -} {n, -}
     std::vector<uint32_t> qnodes;  // 8 words per inner node (quantised form of `nodes`, see quantize_fast_bvh); empty = not quantised
+    std::vector<uint32_t> q4nodes; // 16 words per 4-wide node (build_wide_bvh); empty = not built
+    int32_t root4 = (int32_t)0x80000000;   // root of the 4-wide tree: node index, leaf code or "empty", like `root`
+    uint32_t stack4 = 0;           // deepest traversal stack the 4-wide tree can ask for (entries)
     float qorg[3] = {0, 0, 0};     // decode frame: coordinate = qorg + (2m) * qext, m = 0.5 * (1 + q / 32768) in [0.5, 1)
     float qext[3] = {0, 0, 0};
     int32_t root = (int32_t)0x80000000;
@@ -39,6 +42,17 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err);
 // the reference pads every leaf box by 1e-4 (Bvh.h:16), so quanta of that order cost a few per cent more triangle tests;
 // beyond that the 64-byte float nodes are kept.  Returns whether the quantised form was produced.
 bool quantize_fast_bvh(FastBvh& fb, float max_quantum);
+
+// 4-wide form of the quantised tree, for the wavefront trace kernel: every node holds up to four children, found by
+// repeatedly opening the child with the largest surface area of a binary node's two children (leaves stay leaves, one
+// triangle each, slots unchanged).  A visit then decides four boxes after ONE dependent fetch, and a ray needs about half
+// as many fetch round trips as in the binary tree -- the trace kernel's time goes into waiting for the slowest lane of
+// each round trip.  Record, 64 bytes = two halves in the 32-byte binary format above:
+//   {c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, code0, code1} {c2.x, c2.y, c2.z, c3.x, c3.y, c3.z, code2, code3}
+// same frame (qorg/qext), same outward rounding, absent children = the empty box with the "empty" code.
+// Requires quantize_fast_bvh to have succeeded.  Returns false (and leaves q4nodes empty) when the tree could ask for
+// more than `max_stack` stack entries.
+bool build_wide_bvh(FastBvh& fb, uint32_t max_stack);
 
 // 64-byte triangle records for the kernels: v0 and the ray-independent part of triIntersect (ray-trace-compute.comp:157-173):
 // a = v0 - v1, b = v2 - v0, n = cross(b, a), evaluated here with exactly the fp32 operations the shader performs (no

@@ -1,0 +1,30 @@
+// vcrt_tunables.h -- compile-time knobs of the kernels (override with make EXTRA=-D...; each default is the measured best).
+#pragma once
+
+#define VCRT_BLOCK 128
+#ifndef VCRT_PBLOCK
+#define VCRT_PBLOCK 128   /* persistent kernel: threads per block */
+#endif
+#ifndef VCRT_PMINB
+#define VCRT_PMINB 10    /* persistent kernels: min resident blocks per SM = register cap 48 (r01 A/B on C3: 1 -> 4328, 9 -> 4487, 10 -> 4586, 12 -> 4516 Mrays/s) */
+#endif
+
+#ifndef VCRT_MEGA_MINB
+#define VCRT_MEGA_MINB 1  /* megakernel (A/B variant): it carries the shading state too, no register cap */
+#endif
+#ifndef VCRT_VISITS
+#define VCRT_VISITS 2  /* trace kernel: inner-node visits per lane between two warp votes on the phase switch */
+#endif
+#ifndef VCRT_VISITS4
+#define VCRT_VISITS4 1 /* the same for 4-wide nodes (r01 A/B on C3: 1 -> 6501, 2 -> 6224 Mrays/s in the trace kernel) */
+#endif
+#ifndef VCRT_SMEMRAY
+#define VCRT_SMEMRAY 1   /* trace kernel: ray origin/direction parked in shared memory between triangle tests: no spills at 48 registers (r01 A/B on C3, 4-wide nodes: 6482 -> 6657 Mrays/s; more resident blocks did not pay: 12 blocks 6311) */
+#endif
+#ifndef VCRT_SSTACK
+#define VCRT_SSTACK 0    /* trace kernel: traversal-stack slots per lane kept in shared memory, [slot][thread] (deeper slots: local memory); r01 A/B on C3: 8/16/24 slots all 3-4 % slower than local memory */
+#endif
+#ifndef VCRT_PREFETCH
+#define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
+#endif
+

@@ -80,14 +80,27 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
 
     uint32_t idx = 0xffffffffu;          // ray in flight (0xffffffff: none)
     bool done = false;                   // the queue is exhausted for this lane
+#if VCRT_SMEMRAY
+    // The ray's origin and direction are needed again only by the triangle test (3.6 times per ray on C3): they live in
+    // shared memory, [component][thread] (conflict-free), instead of six registers across the inner-node loop.
+    __shared__ float s_ray[6][VCRT_PBLOCK];
+#endif
     Ray cur; cur.o = cur.d = f3(0, 0, 0);
     TravState t;
     t.idir = t.ood = f3(0, 0, 0); t.closest = VCRT_T_MAX; t.best = -1; t.node = EMPTY; t.sp = 0;
     t.selx = t.sely = t.selz = VCRT_Q15_SEL_LO;
     int32_t pending = EMPTY;             // one postponed leaf
     int32_t tos = EMPTY;                 // top of the traversal stack (vcrt_fast.cuh: trav_inner_step_lean)
-    int32_t stack[VCRT_FAST_STACK];
-    stack[0] = EMPTY;                    // sentinel: popping an exhausted stack yields EMPTY
+    int32_t stack[VCRT_FAST_STACK - VCRT_SSTACK];   // accessed through predicated ld/st.local only (vcrt_fast.cuh: StackRef)
+    StackRef sr;
+    sr.lbase = (uint32_t)__cvta_generic_to_local(stack);
+#if VCRT_SSTACK
+    __shared__ int32_t s_stack[VCRT_SSTACK][VCRT_PBLOCK];
+    sr.sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[0][threadIdx.x]);
+#else
+    sr.sbase = 0u;
+#endif
+    sr.store_if(true, 0, EMPTY);         // sentinel: popping an exhausted stack yields EMPTY
     TraceStats st = {0u, 0u, 0u};
 
     for (;;) {
@@ -107,6 +120,10 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                     cur.o = xyz(o); cur.d = xyz(d);
                 }
                 trav_begin<QN>(t, s, cur);
+#if VCRT_SMEMRAY
+                s_ray[0][threadIdx.x] = cur.o.x; s_ray[1][threadIdx.x] = cur.o.y; s_ray[2][threadIdx.x] = cur.o.z;
+                s_ray[3][threadIdx.x] = cur.d.x; s_ray[4][threadIdx.x] = cur.d.y; s_ray[5][threadIdx.x] = cur.d.z;
+#endif
                 t.sp = 1;
                 tos = EMPTY;
                 if (!valid) { t.node = EMPTY; idx = 0xffffffffu; }   // a path outside the covered extent: nothing to trace or record
@@ -121,14 +138,31 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             // ---- VCRT_VISITS inner-node visits for every lane that has one; a lane that arrives at a leaf postpones it
             //      (one leaf) and keeps traversing
 #pragma unroll
-            for (int v = 0; v < VCRT_VISITS; ++v) {
-                if (t.node >= 0) {
+            for (int v = 0; v < (QN == 2 ? VCRT_VISITS4 : VCRT_VISITS); ++v) {
+                if (QN == 2) {
+                    if (t.node >= 0) {   // 4-wide node: both halves are fetched together, four children decided per round trip
+                        if (COUNT) st.nodes++;
+                        const Words8* p = s.q4nodes + 2 * (size_t)t.node;
+                        const Words8 na = ldg8(p), nb = ldg8(p + 1);
+                        int32_t c[4];
+                        trav_test4(t, na, nb, c);
+                        trav_descend4(t, c, pending, tos, sr);
+                    }
+                } else if (t.node >= 0) {
                     if (COUNT) st.nodes++;
-                    trav_inner_step_lean<QN>(t, s, tos, stack);
+                    float lN, rN;
+                    bool hl, hr;
+                    int32_t cl, cr;
+                    trav_test_children<QN>(t, s, lN, rN, hl, hr, cl, cr);
+                    trav_descend(t, lN, rN, hl, hr, cl, cr, pending, tos, sr);
                 }
-                if ((uint32_t)t.node > 0x80000000u && pending == EMPTY) {   // a leaf (negative and not EMPTY), nothing postponed yet
-                    pending = t.node;
-                    trav_pop(t, tos, stack);
+                {   // a leaf that came off the stack while nothing is postponed: postpone it, go on with the next entry.  Skipped
+                    // (one vote) when no lane needs it: the step reads `tos`, which is usually still in flight from the visit's pop.
+                    const bool park = (uint32_t)t.node > 0x80000000u && pending == EMPTY;
+                    if (__any_sync(FULL, park)) {
+                        pending = park ? t.node : pending;
+                        trav_pop_if(park, t, tos, sr);
+                    }
                 }
             }
             // ---- phase switch.  Common case first, one vote: enough lanes still have an inner node -> go on.  Only below
@@ -143,12 +177,20 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                 // ---- leaf phase: every lane with a postponed leaf tests it
                 if (pending != EMPTY) {
                     if (COUNT) st.tris++;
+#if VCRT_SMEMRAY
+                    Ray lr;
+                    lr.o = f3(s_ray[0][threadIdx.x], s_ray[1][threadIdx.x], s_ray[2][threadIdx.x]);
+                    lr.d = f3(s_ray[3][threadIdx.x], s_ray[4][threadIdx.x], s_ray[5][threadIdx.x]);
+                    trav_leaf_test(t, s, lr, pending);
+#else
                     trav_leaf_test(t, s, cur, pending);
+#endif
                     pending = EMPTY;
                 }
-                if ((uint32_t)t.node > 0x80000000u) {   // the leaf the lane was blocked on becomes the postponed one
-                    pending = t.node;
-                    trav_pop(t, tos, stack);
+                {   // the leaf the lane was blocked on becomes the postponed one
+                    const bool park = (uint32_t)t.node > 0x80000000u;
+                    pending = park ? t.node : pending;
+                    trav_pop_if(park, t, tos, sr);
                 }
                 continue;
             }
