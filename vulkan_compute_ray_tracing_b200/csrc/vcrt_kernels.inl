@@ -122,7 +122,7 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, 
     const int ci = count ? 1 : 0, qi = a.scene.q4nodes ? 2 : a.scene.qnodes ? 1 : 0;
     const uint32_t items = a.owned_tiles * 1024u;
     const uint32_t per_batch = w.capacity / a.sample_count;   // capacity >= sample_count is guaranteed by the caller
-    const uint32_t shade_grid = (uint32_t)sms * 8u;
+    const uint32_t shade_grid = (uint32_t)sms * VCRT_SHADE_GRID;
     for (uint32_t item0 = 0; item0 < items; item0 += per_batch) {
         WfBatch b;
         b.item0 = item0;

@@ -24,6 +24,12 @@
 #ifndef VCRT_SSTACK
 #define VCRT_SSTACK 0    /* trace kernel: traversal-stack slots per lane kept in shared memory, [slot][thread] (deeper slots: local memory); r01 A/B on C3: 8/16/24 slots all 3-4 % slower than local memory */
 #endif
+#ifndef VCRT_SHADE_MINB
+#define VCRT_SHADE_MINB 1  /* shade kernel: min resident blocks (of 256) per SM; 1 = no register cap (60 registers).  r01 A/B on C3 at 32 spp, whole pipeline: 1 -> 5649, 5 (48 registers) -> 5522, 6 -> 5445, 8 -> 5386 Mrays/s */
+#endif
+#ifndef VCRT_SHADE_GRID
+#define VCRT_SHADE_GRID 8u /* shade kernel: blocks per SM in the grid-stride launch (8 vs 20: no difference) */
+#endif
 #ifndef VCRT_PREFETCH
 #define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
 #endif

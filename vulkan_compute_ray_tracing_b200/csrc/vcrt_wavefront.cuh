@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
 
 // ---- shade: one thread per traced ray (ray_color body, ray-trace-compute.comp:321-340)
 template <int SHADER, int RNG_MODE, int TRIG, bool PRIMARY>
-__global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
+__global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __grid_constant__ KernelArgs a, const WfQueues w, const WfBatch b) {
     const SceneView& s = a.scene;
     const uint32_t count = PRIMARY ? b.npaths : w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
