@@ -10,14 +10,17 @@ region.
 
   value     whole-job Mrays/s with the scene resident in HBM; timed per step with CUDA events on the launch stream
             (L2 flushed between steps), max over ranks.
-  e2e       the same metric through the public API with HOST buffers: every step uploads the five scene buffers from
-            pinned host memory (incl. the repack for the fast traversal), renders, resolves and reads the rgba8 target
-            back; wall clock between synchronised barriers, max over ranks.
+  e2e       the same metric through the public API with HOST buffers, following the reference's frame loop: per step the
+            32-byte UBO goes host -> device, the frame is rendered and resolved, and the rgba8 target is read back into
+            pinned host memory (scene resident, as after the reference's initScene); `with_scene_upload` also re-uploads the
+            five scene buffers and rebuilds the traversal records every step.  Wall clock between synchronised barriers,
+            max over ranks.
   roofline  HBM-bound traversal roofline for the dominant kernel (wf_trace_kernel, timed per launch with CUDA events on
             its stream inside the timed region): algorithmic bytes per ray B_ray = 48*(nodes + triangles) of the canonical
             (reference-order, t-culled) traversal, counted by the CPU oracle on a tile sample of the same ray set
             (SURVEY.md 8d).  The kernel walks a SAH tree rebuilt over the same leaves and fetches far fewer bytes, so
-            `frac` exceeds 1; `own_*` gives the bytes the kernel actually requests (its own node/triangle counters).
+            `frac` exceeds 1; `own_*` gives the bytes the kernel actually requests (its own node/triangle counters) and
+            `l1_gather` the kernel's 32-byte gather rate against the L1TEX gather ceiling measured by tools/ubench.
   cpu_baseline / --impl reference
             the reference's own shader text compiled for the CPU (oracle/_ref, kind "reference"; falls back to the
             restated oracle, kind "port") on all host cores, on a bounded sample of the same workload.
@@ -37,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 CAM = (1.8, 8.6, 1.1)   # main.cpp:37
 HBM_FALLBACK_GBS = 6650.0
+L1_GATHER_PEAK_G = 270.0   # measured: profiles/r01_v10_gather_tex_ubench.log (modes L / LL, 32 MB and 2 MB record sets)
 
 
 def measured_peak():
@@ -390,10 +394,17 @@ def main():
         model.renderCommand(None, 0, cp)
         cc = mat.counters()
         node_bytes = 32 if mat.getInfo("fast_nodes") == "q15" else 64
-        own_bray = (node_bytes * cc.nodes + 48 * cc.triangles) / max(cc.rays, 1)
+        tri_bytes = 64                                  # the traversal's triangle record (two 256-bit loads per test)
+        own_bray = (node_bytes * cc.nodes + tri_bytes * cc.triangles) / max(cc.rays, 1)
+        # the memory-side ceiling that actually binds the kernel: 32-byte gathers through L1TEX;
+        # peak = dependent random 32-byte gathers missing L1, tools/ubench/gather_tex.cu on this GPU model (profiles/r01_v10_gather_tex_ubench.log)
+        gathers_per_ray = (node_bytes // 32) * cc.nodes / max(cc.rays, 1) + 2.0 * cc.triangles / max(cc.rays, 1) + 1.0
+        g_rate = gathers_per_ray * rays_per_launch / kernel_s / 1e9
         own = {"own_bytes_per_ray": own_bray, "own_nodes_per_ray": cc.nodes / max(cc.rays, 1), "own_tris_per_ray": cc.triangles / max(cc.rays, 1),
-               "own_node_bytes": node_bytes, "own_achieved": own_bray * rays_per_launch / kernel_s / 1e9,
-               "own_frac": own_bray * rays_per_launch / kernel_s / 1e9 / peak}
+               "own_node_bytes": node_bytes, "own_tri_bytes": tri_bytes, "own_achieved": own_bray * rays_per_launch / kernel_s / 1e9,
+               "own_frac": own_bray * rays_per_launch / kernel_s / 1e9 / peak,
+               "l1_gather": {"gathers_per_ray": gathers_per_ray, "achieved": g_rate, "peak": L1_GATHER_PEAK_G, "unit": "G 32-byte gathers/s",
+                             "frac": g_rate / L1_GATHER_PEAK_G, "peak_source": "tools/ubench/gather_tex.cu, L1-missing chains, B200"}}
         line = {"metric": "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, scene), "clocks": clocks, "gpu_launches": total_launches,
@@ -418,4 +429,15 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one line, the JSON result: anything libraries print on the way (e.g. NCCL's version banner)
+    # goes to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):   # noqa: A001 -- the result line goes to the real stdout
+        sys.stdout.flush()
+        os.write(_real_stdout, (" ".join(str(x) for x in a) + "\n").encode())
+
     main()

@@ -143,6 +143,29 @@ def test_c2_glass_scene_1080p(oracle, doge_glass):
     assert same_bits(rest, full)
 
 
+@pytest.mark.parametrize("fmt", ["q15x4", "q15", "f32"])
+def test_node_formats_bit_exact(oracle, fmt):
+    """Every node format of the fast traversal (4-wide quantised = the default, binary quantised, 64-byte float) through
+    the wavefront trace kernel and the one-thread-per-pixel kernel: boxes only cull, so every output bit equals the
+    reference traversal's; the format actually in use is read back through vcrt_get_info."""
+    from gpuharness import GpuScene
+    sc = small_scene(n_tris=6000, seed=21)
+    cam = (0.0, 6.0, 1.5)
+    g = GpuScene(sc, 256, 192)
+    g.material.setOption("fast_nodes", fmt)
+    kw = dict(shader="full", max_bounces=6, sample_count=2, accum="f32", trig="portable", rng="philox", stack_depth=64)
+    a = oracle.render(sc, cam, 256, 192, make_params(traversal="reference", **kw), want_aov=True)
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    for trav in ("fast", "fast_static"):
+        args = dict(kw, **trav_kw(trav))
+        args["flags"] = args.get("flags", 0) | vcrt.FLAG_COUNT_TRAVERSAL
+        b = g.render(cam, want_aov=True, **args)
+        assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (fmt, trav)
+        assert a["counters"].rays == b["counters"].rays and b["counters"].nodes > 0
+    assert g.material.getInfo("fast_nodes") == fmt
+    g.close()
+
+
 def test_glass_metal_deep_tree(oracle):
     from gpuharness import GpuScene
     sc = small_scene(n_tris=5000, seed=5)

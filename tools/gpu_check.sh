@@ -12,5 +12,6 @@ timeout 300 python tools/sweep.py --spp 16 --count --trace >> $out/ab.log 2>&1
 if [ "$2" != "quick" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:wf_trace_kernel --launch-skip 8 -c 3 -o $out/trace_full -f python tools/sweep.py --spp 8 --reps 1 > $out/ncu_full.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:wf_trace_kernel --csv --log-file $out/traffic.csv python tools/sweep.py --spp 64 --reps 0 > $out/traffic.log 2>&1
 fi
 ls -la $out
