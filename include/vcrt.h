@@ -166,11 +166,12 @@ int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile
 
 /* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
  * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
- * (default: 32-byte quantised nodes when the scene extent allows, else 64-byte float nodes), "q15", "f32"; "wf_batch_paths":
+ * (default: 4-wide quantised 64-byte nodes when the scene extent allows, else binary 64-byte float nodes), "q15x4" (4-wide quantised
+ * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "wf_batch_paths":
  * paths per wavefront batch (queue memory: 120 B per path); "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 
-/* Read-only facts about ctx as text: "fast_nodes" -> "q15" | "f32" | "none" (what the fast traversal walks after the last
+/* Read-only facts about ctx as text: "fast_nodes" -> "q15x4" | "q15" | "f32" | "none" (what the fast traversal walks after the last
  * upload), "fast_node_count", "fast_depth", "wf_batch_paths", "device".  Builds the fast records if they are stale. */
 int vcrt_get_info(vcrt_ctx* ctx, const char* key, char* value, size_t capacity);
 

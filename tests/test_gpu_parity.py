@@ -258,6 +258,19 @@ def test_resolve_and_gamma(gpu_doge):
     assert np.abs(img[..., :3].astype(int) - want.astype(int)).max() <= 1
 
 
+def test_long_frame_loop_keeps_counting(doge):
+    """A caller that renders frame after frame and reads the counters only at the end (the reference's mainLoop never reads
+    any): timing events of finished frames are folded in on the way, nothing is lost and the frames still accumulate."""
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 64, 64)
+    g.material.resetCounters()
+    got = g.frames(CAM, 600)
+    c = g.material.counters()
+    assert c.launches == 600 and c.kernel_ms > 0.0 and c.rays > 0
+    assert got.shape == (64, 64, 4) and int(got[..., 3].min()) == 255
+    g.close()
+
+
 def test_error_behaviour(doge):
     import ctypes as C
     import vulkan_compute_ray_tracing_b200 as vcrt

@@ -253,7 +253,7 @@ class ComputeMaterial:
         self._check(N.lib().vcrt_unpack_tiles(self._ctx, what, tile_rank, tile_count, C.c_void_p(packed_ptr), nbytes))
 
     def getInfo(self, key):
-        """Read-only facts as text, e.g. getInfo("fast_nodes") -> "q15" | "f32" | "none"."""
+        """Read-only facts as text, e.g. getInfo("fast_nodes") -> "q15x4" | "q15" | "f32" | "none"."""
         self._require()
         buf = C.create_string_buffer(64)
         self._check(N.lib().vcrt_get_info(self._ctx, key.encode(), buf, 64))

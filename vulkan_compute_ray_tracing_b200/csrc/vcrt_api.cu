@@ -270,6 +270,21 @@ int vcrt_set_ubo(vcrt_ctx* c, const vcrt_ubo* ubo) {
     return VCRT_OK;
 }
 
+// Folds the timing events of renders that have already finished into the counters, without waiting for anything: keeps
+// the event lists short for callers that render frame after frame and never read the counters.
+static void harvest_events(vcrt_ctx* c) {
+    size_t done = 0;
+    while (done < c->events.size() && cudaEventQuery(c->events[done].second) == cudaSuccess) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, c->events[done].first, c->events[done].second) == cudaSuccess) c->kernel_ms += ms;
+        cudaEventDestroy(c->events[done].first);
+        cudaEventDestroy(c->events[done].second);
+        ++done;
+    }
+    c->events.erase(c->events.begin(), c->events.begin() + (long)done);
+    c->trace_timer.harvest(&c->trace_ms, &c->trace_launches);
+}
+
 static int prepare_fast(vcrt_ctx* c) {
     if (c->fast_dirty) {
         FastBvh fb;
@@ -379,6 +394,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     CU(c, cudaEventRecord(e1, c->stream), "record event");
     c->events.emplace_back(e0, e1);
     c->launches += nlaunch;
+    if (c->events.size() >= 256 || c->trace_timer.pending.size() >= 2048) harvest_events(c);   // a frame loop that never asks for counters
     return VCRT_OK;
 }
 

@@ -37,6 +37,17 @@ struct TraceTimer {
         }
         pending.clear();
     }
+    // the same for the launches that have already finished, without a synchronise
+    void harvest(double* ms, uint64_t* n) {
+        size_t done = 0;
+        while (done < pending.size() && cudaEventQuery(pending[done].second) == cudaSuccess) {
+            float f = 0.0f;
+            if (cudaEventElapsedTime(&f, pending[done].first, pending[done].second) == cudaSuccess) { *ms += f; ++*n; }
+            pool.push_back(pending[done].first); pool.push_back(pending[done].second);
+            ++done;
+        }
+        pending.erase(pending.begin(), pending.begin() + (long)done);
+    }
     void destroy() {
         for (auto& p : pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         for (cudaEvent_t e : pool) cudaEventDestroy(e);
