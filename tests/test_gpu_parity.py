@@ -258,6 +258,46 @@ def test_resolve_and_gamma(gpu_doge):
     assert np.abs(img[..., :3].astype(int) - want.astype(int)).max() <= 1
 
 
+def test_c3_full_size_properties(oracle):
+    """BASELINE.json configs[2] at full size (999 158 triangles, 1920x1080, depth 8), where the oracle cannot render the
+    whole frame in seconds: (1) the oracle on 1/64 of the tiles, bit-exact (portable trig); (2) four independent
+    traversals -- the wavefront kernel over the 4-wide tree, over the binary quantised tree, over float nodes, and the
+    one-thread-per-pixel kernel -- agree on every bit of the full frame and on the ray count; (3) tile shards partition the
+    frame; (4) a render continued on top of its first half equals the uninterrupted one."""
+    from gpuharness import GpuScene
+    from vulkan_compute_ray_tracing_b200 import scenegen
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    sc = scenegen.generate_box_scene(1000000, seed=1234)
+    w, h = 1920, 1080
+    g = GpuScene(sc, w, h)
+    kw = dict(shader="full", max_bounces=8, sample_count=2, accum="f32", rng="philox", trig="portable", stack_depth=64)
+    full = g.render(CAM, traversal="fast", want_aov=True, **kw)
+    assert g.material.getInfo("fast_nodes") == "q15x4"
+    # (1) the oracle on every 64th tile
+    a = oracle.render(sc, CAM, w, h, make_params(traversal="reference", tile_rank=5, tile_count=64, **kw), want_aov=True)
+    b = g.render(CAM, traversal="fast", want_aov=True, tile_rank=5, tile_count=64, **kw)
+    assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"])
+    assert a["counters"].rays == b["counters"].rays
+    own = a["accumf"][..., 3] > 0
+    assert own.any() and same_bits(full["accumf"][own], a["accumf"][own]) and same_bits(full["aov"][own], a["aov"][own])
+    # (2) independent traversals
+    for fmt, flags in (("q15", 0), ("f32", 0), ("q15x4", vcrt.FLAG_STATIC_KERNEL)):
+        g.material.setOption("fast_nodes", fmt)
+        o = g.render(CAM, traversal="fast", want_aov=True, flags=flags, **kw)
+        assert same_bits(o["accumf"], full["accumf"]) and same_bits(o["aov"], full["aov"]), (fmt, flags)
+        assert o["counters"].rays == full["counters"].rays
+    g.material.setOption("fast_nodes", "auto")
+    # (3) tile shards
+    parts = [g.render(CAM, traversal="fast", tile_rank=r, tile_count=3, **kw)["accumf"] for r in range(3)]
+    assert same_bits(sum(parts), full["accumf"])
+    # (4) resume
+    half = dict(kw, sample_count=1)
+    g.render(CAM, traversal="fast", **half)
+    rest = g.render(CAM, traversal="fast", sample_begin=1, clear=False, **half)["accumf"]
+    assert same_bits(rest, full["accumf"])
+    g.close()
+
+
 def test_long_frame_loop_keeps_counting(doge):
     """A caller that renders frame after frame and reads the counters only at the end (the reference's mainLoop never reads
     any): timing events of finished frames are folded in on the way, nothing is lost and the frames still accumulate."""
