@@ -95,9 +95,13 @@ def pinned_copy(arr):
 
 
 def build_workload(args):
-    from vulkan_compute_ray_tracing_b200 import scenegen
     t0 = time.time()
-    scene = scenegen.generate_box_scene(args.triangles, seed=args.scene_seed)
+    if args.config == "c2":   # BASELINE.json configs[1]: the bundled scene (glass/metal variant, as assembled by csrc/scene from the reference's OBJ files)
+        import vulkan_compute_ray_tracing_b200 as vcrt
+        scene = vcrt.load_scene(os.path.join(ROOT, "tests", "golden", "doge_glass_scene.vcrt"))
+    else:
+        from vulkan_compute_ray_tracing_b200 import scenegen
+        scene = scenegen.generate_box_scene(args.triangles, seed=args.scene_seed)
     return scene, time.time() - t0
 
 
@@ -172,6 +176,7 @@ def run_reference_arm(args, rank):
 
 # BASELINE.json configs[2..4].  c3 is the headline (weak scaling: 64 spp per GPU); c4 and c5 are fixed-size jobs (strong scaling).
 CONFIGS = {
+    "c2": dict(triangles=0, width=1920, height=1080, spp=16, sharding="samples", scaling="weak"),
     "c3": dict(triangles=1000000, width=1920, height=1080, spp=64, sharding="samples", scaling="weak"),
     "c4": dict(triangles=10000000, width=3840, height=2160, spp=16, sharding="tiles", scaling="strong"),
     "c5": dict(triangles=1000000, width=3840, height=2160, spp=1024, sharding="samples", scaling="strong"),
@@ -181,8 +186,10 @@ CONFIGS = {
 def workload_config(args, scene):
     spp_txt = "%d spp/GPU" % args.spp if args.scaling == "weak" else "%d spp in total" % args.spp
     shard = {"samples": "sample slices + NCCL reduce of the f32 accumulation buffers", "tiles": "32x32 tile interleave + NCCL all-gather of packed rgba8 tiles"}[args.sharding]
-    return {"workload": "%s: synthetic %d-triangle lit box (seed %d), %dx%d, %s, depth %d, full shader, philox, f32 accum, fast traversal"
-                        % (args.config.upper(), len(scene["triangles"]) // 48, args.scene_seed, args.width, args.height, spp_txt, args.bounces),
+    what = "bundled scene, glass/metal variant (%d triangles)" % (len(scene["triangles"]) // 48) if args.config == "c2" else \
+        "synthetic %d-triangle lit box (seed %d)" % (len(scene["triangles"]) // 48, args.scene_seed)
+    return {"workload": "%s: %s, %dx%d, %s, depth %d, full shader, philox, f32 accum, fast traversal"
+                        % (args.config.upper(), what, args.width, args.height, spp_txt, args.bounces),
             "triangles": len(scene["triangles"]) // 48, "bvh_nodes": len(scene["bvh"]) // 48, "width": args.width, "height": args.height,
             "spp": args.spp, "spp_is": "per GPU" if args.scaling == "weak" else "total", "max_bounces": args.bounces,
             "sharding": (shard + " (%s)" % args.scaling) if args.gpus > 1 else "none",
@@ -195,7 +202,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json workload: c3 (headline), c4, c5")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json workload: c3 (headline), c2, c4, c5")
     ap.add_argument("--triangles", type=int, default=None)
     ap.add_argument("--scene-seed", type=int, default=1234)
     ap.add_argument("--width", type=int, default=None)
@@ -363,6 +370,28 @@ def main():
         v, ms = timed(False, args.steps)
         e2e = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
                "protocol": "reference frame loop: UBO write + computeCommand-equivalent render + resolve + rgba8 read-back to pinned host memory; scene resident"}
+        # the reference's own unit of work, "ms/frame" (main.cpp:397-413): one 1-spp frame per iteration of the frame loop --
+        # UBO with the frame's sample index in, one sample rendered on top of the accumulation, resolve, rgba8 frame back
+        one = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
+                                 stack_depth=64, sample_begin=0, sample_count=1, philox_seed=args.scene_seed)
+        if world == 1:
+            def one_frame(k):
+                ubo.buffers[0].write(vcrt.pack_ubo(CAM, k, scene))
+                one.sample_begin = k
+                model.renderCommand(None, 0, one)
+                mat.resolve(k + 1, 0.0)
+                mat._check(L.vcrt_read_target_rgba8(mat._ctx, out_host.ctypes.data, out_host.nbytes))
+            mat.clearAccum()
+            for k in range(4):
+                one_frame(k)
+            mat.resetCounters()
+            nfr = 32
+            t0 = time.perf_counter()
+            for k in range(4, 4 + nfr):
+                one_frame(k)
+            dt = time.perf_counter() - t0
+            e2e["frame_1spp"] = {"ms_per_frame": 1e3 * dt / nfr, "value": mat.counters().rays / dt / 1e6, "unit": "Mrays/s", "frames": nfr,
+                                 "protocol": "progressive frame loop, one sample per frame, rgba8 frame read back every frame"}
         v, ms = timed(True, min(args.steps, 3))
         e2e["with_scene_upload"] = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
                                     "includes": "upload of the 5 scene buffers from pinned host memory + host rebuild of the traversal records, every step"}
@@ -416,7 +445,7 @@ def main():
                 "rays_per_step": total_rays / args.steps, "scene_build_s": gen_s}
         if e2e:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline and args.config == "c3":
+        if world == 1 and not args.no_cpu_baseline and args.config in ("c2", "c3"):
             dt1, rays1, kind = cpu_reference_step(scene, w, h, args.bounces, 1)
             frames = int(min(max(round(15.0 / max(dt1, 1e-3)), 1), 16))
             dt, r, kind = cpu_reference_step(scene, w, h, args.bounces, frames, first_sample=1)
