@@ -298,6 +298,20 @@ def test_c3_full_size_properties(oracle):
     g.close()
 
 
+def test_batching_does_not_change_results(gpu_doge):
+    """The wavefront pipeline cuts a call into batches of whole pixels (option wf_batch_paths); any batch size gives the same
+    bits, ragged last batch and batches smaller than a tile included."""
+    kw = dict(shader="full", traversal="fast", max_bounces=6, sample_count=3, accum="f32", rng="philox", trig="libm")
+    want = gpu_doge.render(CAM, **kw)
+    default = gpu_doge.material.getInfo("wf_batch_paths")
+    for batch in (1024, 7 * 1024 + 3, 100000):
+        gpu_doge.material.setOption("wf_batch_paths", str(batch))
+        got = gpu_doge.render(CAM, **kw)
+        assert same_bits(got["accumf"], want["accumf"]) and got["counters"].rays == want["counters"].rays, batch
+        assert got["counters"].launches > want["counters"].launches
+    gpu_doge.material.setOption("wf_batch_paths", default)
+
+
 def test_long_frame_loop_keeps_counting(doge):
     """A caller that renders frame after frame and reads the counters only at the end (the reference's mainLoop never reads
     any): timing events of finished frames are folded in on the way, nothing is lost and the frames still accumulate."""

@@ -1,3 +1,2 @@
-mkdir -p gpurun_out/v24
-python bench.py --config c2 > gpurun_out/v24/bench_c2.json 2> gpurun_out/v24/bench_c2.err; tail -c 1500 gpurun_out/v24/bench_c2.json; tail -3 gpurun_out/v24/bench_c2.err
-python bench.py --no-cpu-baseline > gpurun_out/v24/bench_c3.json 2> gpurun_out/v24/bench_c3.err; tail -c 1200 gpurun_out/v24/bench_c3.json; tail -3 gpurun_out/v24/bench_c3.err
+mkdir -p gpurun_out/v26
+python tools/sweep.py --spp 64 --reps 3 --trace wf_batch_paths=33554432,67108864,140000000 2>&1 | tee gpurun_out/v26/batch.log
