@@ -1,2 +1,2 @@
-mkdir -p gpurun_out/v26
-python tools/sweep.py --spp 64 --reps 3 --trace wf_batch_paths=33554432,67108864,140000000 2>&1 | tee gpurun_out/v26/batch.log
+mkdir -p gpurun_out/v28
+bash tools/ab_libs.sh "lib lib_spf lib_spf2 lib lib_spf lib_spf2" --spp 64 --trace 2>&1 | tee gpurun_out/v28/ab.log
