@@ -312,6 +312,24 @@ def test_batching_does_not_change_results(gpu_doge):
     gpu_doge.material.setOption("wf_batch_paths", default)
 
 
+def test_headless_render_cli(gpu_doge, tmp_path):
+    """python -m vulkan_compute_ray_tracing_b200.render: the EXR holds the linear mean of the samples the API returns, the
+    PPM the post-processed 8-bit frame."""
+    from vulkan_compute_ray_tracing_b200 import imageio, render
+    scene_path = os.path.join(GOLDEN, "doge_scene.vcrt")
+    kw = dict(shader="full", traversal="fast", max_bounces=8, sample_count=4, accum="f32", rng="philox")
+    want = gpu_doge.render(CAM, **kw)["accumf"]
+    assert render.main([scene_path, str(tmp_path / "o.exr"), "--width", "800", "--height", "600", "--spp", "4"]) == 0
+    got = imageio.read_exr(tmp_path / "o.exr")
+    assert same_bits(got, np.ascontiguousarray(want[..., :3] / 4.0))
+    assert render.main([scene_path, str(tmp_path / "o.ppm"), "--width", "800", "--height", "600", "--spp", "4"]) == 0
+    raw = (tmp_path / "o.ppm").read_bytes()
+    assert raw.startswith(b"P6\n800 600\n255\n")
+    img = np.frombuffer(raw[len(b"P6\n800 600\n255\n"):], np.uint8).reshape(600, 800, 3)
+    ref = np.rint(np.clip(want[..., :3] / 4.0, 0, 1) * 255.0) / 255.0
+    assert np.abs(img.astype(int) - np.rint(ref ** (1 / 2.2) * 255.0).astype(int)).max() <= 1
+
+
 def test_long_frame_loop_keeps_counting(doge):
     """A caller that renders frame after frame and reads the counters only at the end (the reference's mainLoop never reads
     any): timing events of finished frames are folded in on the way, nothing is lost and the frames still accumulate."""

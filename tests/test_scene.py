@@ -88,3 +88,36 @@ def test_synthetic_scene_is_deterministic_and_lit(scenegen, oracle):
     assert 0.95 * 20000 <= n <= 20000 and len(a["bvh"]) // 48 == 2 * n - 1 and len(a["lights"]) // 8 == 2
     img = oracle.render(a, (1.8, 8.6, 1.1), 96, 64, make_params(shader="full", max_bounces=8, stack_depth=64, accum="f32", sample_count=4))["accumf"]
     assert img[..., :3].mean() > 0.02          # the emitter lights the box
+
+
+def test_image_writers_roundtrip(tmp_path):
+    """Headless dumps: PPM / PFM byte layout and the uncompressed scanline OpenEXR subset (header attributes, offset table,
+    B-G-R planar scanlines) read back exactly."""
+    import struct
+    from vulkan_compute_ray_tracing_b200 import imageio
+    rng = np.random.default_rng(3)
+    img = rng.random((5, 7, 4)).astype(np.float32) * 3.0
+    imageio.write_exr(tmp_path / "a.exr", img)
+    back = imageio.read_exr(tmp_path / "a.exr")
+    assert back.shape == (5, 7, 3) and np.array_equal(back, img[..., :3])
+    blob = (tmp_path / "a.exr").read_bytes()
+    assert blob[:4] == bytes([0x76, 0x2F, 0x31, 0x01]) and blob[4:8] == b"\x02\0\0\0"
+    assert b"channels\0chlist\0" in blob and b"dataWindow\0box2i\0" in blob and b"compression\0compression\0" in blob
+    first = struct.unpack_from("<Q", blob, blob.index(b"screenWindowWidth") + len(b"screenWindowWidth\0float\0") + 8 + 1)[0]
+    assert struct.unpack_from("<ii", blob, first) == (0, 3 * 7 * 4) and len(blob) == first + 5 * (8 + 3 * 7 * 4)
+    imageio.write_pfm(tmp_path / "a.pfm", img)
+    raw = (tmp_path / "a.pfm").read_bytes()
+    assert raw.startswith(b"PF\n7 5\n-1.0\n") and np.array_equal(np.frombuffer(raw[len(b"PF\n7 5\n-1.0\n"):], "<f4").reshape(5, 7, 3)[::-1], img[..., :3])
+    u8 = (rng.random((4, 6, 4)) * 255).astype(np.uint8)
+    imageio.write_ppm(tmp_path / "a.ppm", u8)
+    raw = (tmp_path / "a.ppm").read_bytes()
+    assert raw.startswith(b"P6\n6 4\n255\n") and raw[len(b"P6\n6 4\n255\n"):] == u8[..., :3].tobytes()
+    try:
+        import os
+        os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+        import cv2
+        cvimg = cv2.imread(str(tmp_path / "a.exr"), cv2.IMREAD_UNCHANGED)
+    except Exception:
+        cvimg = None
+    if cvimg is not None:                     # an independent decoder, when this OpenCV build has one
+        assert np.array_equal(cvimg[..., ::-1], img[..., :3])

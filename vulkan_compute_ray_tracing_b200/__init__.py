@@ -3,6 +3,7 @@ compute shader, behind the reference's ComputeMaterial / ComputeModel interface.
 from .api import (ACCUM, AOV_DTYPE, FLAG_COUNT_TRAVERSAL, FLAG_MEGAKERNEL, FLAG_STATIC_KERNEL, FLAG_REF_DISPATCH_COVERAGE, FLAG_WRITE_AOV, RNG, SHADER, TRAVERSAL, TRIG,
                   VK_SHADER_STAGE_COMPUTE_BIT, Buffer, BufferBundle, BufferUtils, ComputeMaterial, ComputeModel, Image,
                   VcrtError, render_params)
+from . import imageio
 from .frameloop import Camera, FrameLoop
 from .scene import CAMERA_START, load_scene, pack_ubo, save_scene
 
