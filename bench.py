@@ -183,6 +183,21 @@ CONFIGS = {
 }
 
 
+_HASH = {}
+
+
+def scene_hash(scene):
+    """sha256 over the five reference-layout buffers in binding order (the bytes both arms render)."""
+    key = id(scene)
+    if key not in _HASH:
+        import hashlib
+        h = hashlib.sha256()
+        for name in ("triangles", "materials", "bvh", "lights", "spheres"):
+            h.update(np.ascontiguousarray(scene[name]).tobytes())
+        _HASH[key] = h.hexdigest()[:16]
+    return _HASH[key]
+
+
 def workload_config(args, scene):
     spp_txt = "%d spp/GPU" % args.spp if args.scaling == "weak" else "%d spp in total" % args.spp
     shard = {"samples": "sample slices + NCCL reduce of the f32 accumulation buffers", "tiles": "32x32 tile interleave + NCCL all-gather of packed rgba8 tiles"}[args.sharding]
@@ -192,6 +207,7 @@ def workload_config(args, scene):
                         % (args.config.upper(), what, args.width, args.height, spp_txt, args.bounces),
             "triangles": len(scene["triangles"]) // 48, "bvh_nodes": len(scene["bvh"]) // 48, "width": args.width, "height": args.height,
             "spp": args.spp, "spp_is": "per GPU" if args.scaling == "weak" else "total", "max_bounces": args.bounces,
+            "scene_sha256": scene_hash(scene),
             "sharding": (shard + " (%s)" % args.scaling) if args.gpus > 1 else "none",
             "l2": "flushed between timed steps (256 MiB memset)"}
 
