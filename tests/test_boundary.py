@@ -115,3 +115,18 @@ def test_camera_matches_reference_defaults():
     assert np.allclose(c.Position - p0, (-0.25, 0.5, -0.25), atol=1e-6)
     c.ProcessKeyboard(".", 1.0)
     assert np.allclose(c.Position - p0, (-0.25, 0.5, -0.25), atol=1e-6)
+
+
+def build_cpp_example(dst):
+    """examples/headless_main.cpp (the reference's main.cpp without the window) against the header-only facade + libvcrt.so."""
+    lib_dir = os.path.join(ROOT, "vulkan_compute_ray_tracing_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", str(dst), os.path.join(ROOT, "examples", "headless_main.cpp"),
+                           "-L", lib_dir, "-lvcrt", "-Wl,-rpath," + lib_dir])
+    return str(dst)
+
+
+def test_cpp_facade_example_builds(tmp_path):
+    exe = build_cpp_example(tmp_path / "headless_main")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode != 0 and "usage:" in out.stderr          # no arguments: usage text, EXIT_FAILURE (no device touched)
+

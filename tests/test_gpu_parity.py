@@ -330,6 +330,27 @@ def test_headless_render_cli(gpu_doge, tmp_path):
     assert np.abs(img.astype(int) - np.rint(ref ** (1 / 2.2) * 255.0).astype(int)).max() <= 1
 
 
+def test_cpp_example_matches_python_frames(tmp_path):
+    """examples/headless_main.cpp -- the reference's frame loop written against include/vcrt/ComputeMaterial.hpp -- renders
+    the same rgba8 frames as the Python mirror of the same classes (both are thin layers over the C ABI)."""
+    import subprocess
+    from gpuharness import GpuScene
+    from test_boundary import build_cpp_example
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    exe = build_cpp_example(tmp_path / "headless_main")
+    scene_path = os.path.join(GOLDEN, "doge_scene.vcrt")
+    out = subprocess.run([exe, scene_path, str(tmp_path / "o.ppm"), "3", "320", "200"], capture_output=True, text=True)
+    assert out.returncode == 0 and "ms/frame" in out.stdout, out.stderr
+    raw = (tmp_path / "o.ppm").read_bytes()
+    hdr = b"P6\n320 200\n255\n"
+    assert raw.startswith(hdr)
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(200, 320, 3)
+    g = GpuScene(vcrt.load_scene(scene_path), 320, 200)
+    want = g.frames(CAM, 3)
+    g.close()
+    assert np.array_equal(img, want[..., :3])
+
+
 def test_long_frame_loop_keeps_counting(doge):
     """A caller that renders frame after frame and reads the counters only at the end (the reference's mainLoop never reads
     any): timing events of finished frames are folded in on the way, nothing is lost and the frames still accumulate."""
