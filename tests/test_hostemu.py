@@ -36,6 +36,24 @@ def test_fast_equals_reference_on_deep_random_trees(oracle, hostemu):
         assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (seed, n)
 
 
+@pytest.mark.parametrize("reserved", [8, 12])
+def test_wide_tree_on_small_and_random_scenes(oracle, hostemu, reserved):
+    """The 4-wide form of the quantised tree (build_wide_bvh) on the awkward sizes -- one to five triangles (root with fewer
+    than four children, a single leaf, no inner node at all), duplicated triangles (ties across sibling leaves), a few
+    hundred random ones with glass and metal: every bit equals the reference traversal's.  `reserved` 8 = automatic
+    quantisation limit, 12 = quantised whatever the scene extent."""
+    cam = (0.0, 6.0, 1.5)
+    for seed, n in ((11, 1), (12, 2), (13, 3), (14, 4), (15, 5), (16, 9), (17, 33), (18, 300), (19, 2000)):
+        sc = small_scene(n_tris=n, seed=seed)
+        kw = dict(shader="full", max_bounces=6, sample_count=2, accum="f32", rng="philox", stack_depth=64)
+        a = oracle.render(sc, cam, 80, 56, make_params(traversal="reference", **kw), want_aov=True)
+        p = make_params(traversal="fast", **kw)
+        p._reserved = reserved
+        b = hostemu.render(sc, cam, 80, 56, p, want_aov=True)
+        assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (seed, n)
+        assert a["counters"].rays == b["rays"]
+
+
 def test_duplicate_triangles_tie_rule(oracle, hostemu):
     """Every triangle duplicated: equal t for both copies; the reference keeps the first leaf in its visiting order."""
     sc = small_scene(n_tris=40, seed=9)
