@@ -37,7 +37,7 @@ def main():
     subprocess.check_call([os.path.join(root, "oracle", "_ref", "ref_scene_dump"), os.path.join(HERE, "doge_scene.vcrt")])
     scene = load_scene(os.path.join(HERE, "doge_scene.vcrt"))
     ref = Ref()
-    for variant, frames in (("full_b2_s16", 1), ("full_b2_s16", 4), ("simple_b4_s16", 1), ("full_b8_s16", 2)):
+    for variant, frames in (("full_b2_s16", 1), ("full_b2_s16", 4), ("simple_b4_s16", 1), ("full_b8_s16", 2), ("full_b4_s16", 1)):
         img = ref.render_frames(variant, scene, CAM, 800, 600, frames)
         Image.fromarray(img, "RGBA").save(os.path.join(HERE, "ref_%s_800x600_f%d.png" % (variant, frames)), optimize=True)
     # the reference's literal dispatch extent (main.cpp:228): floor(W/32) x floor(H/32) groups

@@ -106,6 +106,21 @@ def test_libm_trig_within_tolerance(gpu_doge, oracle, doge):
     assert float((np.abs(a - b) > 1e-3).mean()) < 5e-3
 
 
+def test_c1_config_reference_frame(gpu_doge, oracle, doge):
+    """BASELINE configs[0] exactly: bundled scene, 800x600, 1 spp, max depth 4, as the reference's own shader renders it
+    (golden from oracle/_ref built with NUM_BOUNCES 4).  The CUDA frame is within 1 LSB of the golden on >= 99.9 % of the
+    pixel-channels (libm sinf/cosf), and bit-identical to the oracle in portable-trig mode for the reference-shaped and
+    the fast traversal alike."""
+    want = load_png("ref_full_b4_s16_800x600_f1.png")
+    kw = dict(shader="full", max_bounces=4, sample_count=1, accum="rgba8_ref", rng="pcg_ref")
+    for trav in ("reference", "fast"):
+        got = gpu_doge.render(CAM, traversal=trav, trig="libm", **kw)["target"]
+        assert frac_within_1lsb(got, want) >= 0.999, trav
+        a = oracle.render(doge, CAM, 800, 600, make_params(traversal="reference", trig="portable", **kw))["target"]
+        b = gpu_doge.render(CAM, traversal=trav, trig="portable", **kw)["target"]
+        assert np.array_equal(a, b), trav
+
+
 def test_c2_config_1080p(oracle, doge):
     """BASELINE config 2 shape: bundled scene, 1920x1080, depth 8, light sampling (4 of the 16 spp checked against the oracle)."""
     from gpuharness import GpuScene

@@ -46,6 +46,7 @@ def test_portable_sincos_accuracy(oracle):
     ("ref_full_b2_s16_800x600_f1.png", dict(shader="full", sample_count=1)),
     ("ref_full_b2_s16_800x600_f4.png", dict(shader="full", sample_count=4)),
     ("ref_full_b8_s16_800x600_f2.png", dict(shader="full", max_bounces=8, sample_count=2)),
+    ("ref_full_b4_s16_800x600_f1.png", dict(shader="full", max_bounces=4, sample_count=1)),       # BASELINE configs[0]: 800x600, 1 spp, depth 4
     ("ref_simple_b4_s16_800x600_f1.png", dict(shader="simple", sample_count=1)),
     ("ref_full_b2_s16_800x600_f1_refdispatch.png", dict(shader="full", sample_count=1, flags=1)),
     ("ref_full_b2_s16_800x600_f2_lights1.png", dict(shader="full", sample_count=2, lights_length=1)),
