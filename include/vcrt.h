@@ -167,12 +167,14 @@ int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile
 /* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
  * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
  * (default: 4-wide quantised 64-byte nodes when the scene extent allows, else binary 64-byte float nodes), "q15x4" (4-wide quantised
- * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "wf_batch_paths":
+ * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "dispatch_traversal": what vcrt_dispatch walks -- "auto" (default: the fast tree whenever
+ * the bound tree is at most 13 levels deep, i.e. whenever the shader's 16-entry stack cannot overflow; identical frames), "reference" (always the
+ * literal hit_bvh), "fast"; "wf_batch_paths":
  * paths per wavefront batch (queue memory: 120 B per path); "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 
 /* Read-only facts about ctx as text: "fast_nodes" -> "q15x4" | "q15" | "f32" | "none" (what the fast traversal walks after the last
- * upload), "fast_node_count", "fast_depth", "wf_batch_paths", "device".  Builds the fast records if they are stale. */
+ * upload), "fast_node_count", "fast_depth", "wf_batch_paths", "dispatch_kernel" ("fast" | "reference": what the last vcrt_dispatch walked), "device".  Builds the fast records if they are stale. */
 int vcrt_get_info(vcrt_ctx* ctx, const char* key, char* value, size_t capacity);
 
 /* Run ctx's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores ctx's own stream), so

@@ -366,6 +366,31 @@ def test_cpp_example_matches_python_frames(tmp_path):
     assert np.array_equal(img, want[..., :3])
 
 
+@pytest.mark.parametrize("shader", ["ray-trace-compute", "ray-trace-compute-simple"])
+def test_dispatch_auto_takes_the_fast_traversal(doge, shader):
+    """computeCommand (vcrt_dispatch) walks the fast tree in the one-launch kernel whenever the reference's 16-entry stack
+    cannot overflow on the bound tree -- same hit records by construction, so the frames are identical bit for bit to the
+    literal traversal's; deeper trees keep the literal traversal (its truncation is part of the reference's behaviour)."""
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 800, 600, shader=shader)
+    g.material.setOption("dispatch_traversal", "reference")
+    want = g.frames(CAM, 4)
+    assert g.material.getInfo("dispatch_kernel") == "reference"
+    g.material.setOption("dispatch_traversal", "auto")
+    got = g.frames(CAM, 4)
+    assert g.material.getInfo("dispatch_kernel") == "fast"
+    assert np.array_equal(got, want)
+    got = g.frames(CAM, 2, full_cover=False)          # the reference's floor(W/32) x floor(H/32) dispatch
+    g.material.setOption("dispatch_traversal", "reference")
+    assert np.array_equal(got, g.frames(CAM, 2, full_cover=False))
+    g.close()
+    deep = small_scene(n_tris=20000, seed=3)          # depth > 13: the shader's stack overflows, only the literal traversal reproduces that
+    g = GpuScene(deep, 96, 64, shader=shader)
+    g.frames((0.0, 6.0, 1.5), 1)
+    assert g.material.getInfo("dispatch_kernel") == "reference"
+    g.close()
+
+
 def test_long_frame_loop_keeps_counting(doge):
     """A caller that renders frame after frame and reads the counters only at the end (the reference's mainLoop never reads
     any): timing events of finished frames are folded in on the way, nothing is lost and the frames still accumulate."""

@@ -41,7 +41,9 @@ struct vcrt_ctx {
     DevBuf q4nodes;
     float qorg[3] = {0, 0, 0}, qext[3] = {0, 0, 0};
     DevBuf qnodes;
-    uint32_t fast_depth = 0;
+    uint32_t fast_depth = 0, bound_depth = 0;
+    int dispatch_trav = 0;                // option "dispatch_traversal": 0 "auto" | 1 "reference" | 2 "fast"
+    bool dispatch_fast = false;           // what the last vcrt_dispatch walked
     bool fast_ok = false;
     std::string fast_err;
     DevBuf fnodes, ftris;
@@ -138,6 +140,12 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         if (m != c->fast_nodes) { c->fast_nodes = m; c->fast_dirty = true; }
         return VCRT_OK;
     }
+    if (k == "dispatch_traversal") {
+        const int m = v == "auto" ? 0 : v == "reference" ? 1 : v == "fast" ? 2 : -1;
+        if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: dispatch_traversal must be 'auto', 'reference' or 'fast'");
+        c->dispatch_trav = m;
+        return VCRT_OK;
+    }
     if (k == "host_threads") {   // OpenMP threads of the host-side record build (launchers such as torchrun export OMP_NUM_THREADS=1)
         const int n = atoi(value);
         if (n < 1 || n > 1024) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: host_threads must be 1..1024");
@@ -172,6 +180,7 @@ int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
         else if (k == "fast_node_count") v = std::to_string(ok ? (c->wide ? c->nf4nodes : c->nfnodes) : 0u);
         else v = std::to_string(ok ? c->fast_depth : 0u);
     } else if (k == "wf_batch_paths") v = std::to_string(c->wf_batch);
+    else if (k == "dispatch_kernel") v = c->dispatch_fast ? "fast" : "reference";
     else if (k == "device") v = std::to_string(c->device);
     else return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: unknown key '" + k + "'");
     if (v.size() + 1 > capacity) return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: buffer too small");
@@ -320,6 +329,7 @@ static int prepare_fast(vcrt_ctx* c) {
             c->froot = fb.root;
             c->nfnodes = fb.num_nodes();
             c->fast_depth = fb.depth;
+            c->bound_depth = fb.bound_depth;
         }
     }
     if (!c->fast_ok) return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err);
@@ -371,7 +381,12 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     const bool count = (p.flags & VCRT_FLAG_COUNT_TRAVERSAL) != 0;
     cudaError_t e;
     uint32_t nlaunch = 1;
-    if (p.traversal == VCRT_TRAVERSAL_FAST && !(p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL))) {
+    // A 1-spp frame of a shallow shader (the reference's own frame: NUM_BOUNCES 2 or 4) is one launch of the one-thread-per-pixel
+    // kernel instead of three launches per bounce of the wavefront pipeline: 0.09 instead of 0.59 ms at 800x600 on the bundled
+    // scene, identical results (r01 A/B; with more samples or deeper paths the wavefront pipeline wins at every size).
+    bool one_launch = (p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL)) != 0;
+    if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && a.sample_count == 1u && a.env.max_bounces <= 4u) { a.flags |= VCRT_FLAG_STATIC_KERNEL; one_launch = true; }
+    if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch) {
         // wavefront pipeline: queues sized for a batch of paths (a range of pixels x all samples of the call)
         // batch = as many whole pixels (all samples of the call) as fit wf_batch paths, but no more than the call needs
         const uint64_t need = (uint64_t)a.owned_tiles * 1024u * a.sample_count;
@@ -414,6 +429,23 @@ int vcrt_dispatch(vcrt_ctx* c, uint32_t gx, uint32_t gy, uint32_t gz) {
     p.struct_size = sizeof p;
     p.shader = (uint32_t)c->shader;
     p.traversal = VCRT_TRAVERSAL_REFERENCE;
+    // The literal hit_bvh (16-entry stack, unordered, no culling) or -- same hit records by construction (vcrt_fast.cuh),
+    // 5-6x less time per frame on the bundled scene -- the fast traversal in the one-launch kernel.  "auto" takes the fast one
+    // when the reference's stack cannot overflow on the bound tree (deepest leaf <= 13 <=> at most 8192 triangles with the
+    // reference's builder): past that depth the shader silently drops part of the tree, which only the
+    // literal traversal reproduces.
+    c->dispatch_fast = false;
+    if (c->dispatch_trav != 1) {
+        const size_t ntris = c->ssbo[VCRT_BINDING_TRIANGLES].bytes / sizeof(vcrt_triangle);
+        if (c->dispatch_trav == 2 || ntris <= 8192) {
+            CU(c, cudaSetDevice(c->device), "set device");
+            const bool ok = prepare_fast(c) == VCRT_OK;
+            if (ok && (c->dispatch_trav == 2 || c->bound_depth <= 13)) c->dispatch_fast = true;
+            else if (c->dispatch_trav == 2) return fail(c, VCRT_ERR_INVALID, "vcrt_dispatch: dispatch_traversal=fast but the fast traversal is unavailable: " + c->fast_err);
+            else c->error.clear();
+        }
+    }
+    if (c->dispatch_fast) { p.traversal = VCRT_TRAVERSAL_FAST; p.flags |= VCRT_FLAG_STATIC_KERNEL; }
     p.rng_mode = VCRT_RNG_PCG_REF;
     p.accum_mode = VCRT_ACCUM_RGBA8_REF;
     p.trig_mode = VCRT_TRIG_LIBM;

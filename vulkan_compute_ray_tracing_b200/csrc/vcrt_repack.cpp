@@ -16,7 +16,7 @@ inline float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 }  // namespace
 
 bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle* tris, uint32_t ntris, FastBvh& out, std::string& err) {
-    out.nodes.clear(); out.tris.clear(); out.root = (int32_t)0x80000000; out.depth = 0;
+    out.nodes.clear(); out.tris.clear(); out.root = (int32_t)0x80000000; out.depth = 0; out.bound_depth = 0;
     if (nbvh == 0) return true;
     const float inf = std::numeric_limits<float>::infinity();
     std::vector<uint8_t> seen(nbvh, 0);
@@ -74,6 +74,7 @@ bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle
             }
         }
     }
+    out.bound_depth = out.depth;
     if (out.depth + 3 > 48) { err = "bvh: depth " + std::to_string(out.depth) + " exceeds the fast traversal stack (45)"; return false; }
     return true;
 }

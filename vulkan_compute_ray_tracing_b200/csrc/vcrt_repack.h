@@ -19,6 +19,7 @@ struct FastBvh {
     float qext[3] = {0, 0, 0};
     int32_t root = (int32_t)0x80000000;
     uint32_t depth = 0;            // deepest leaf (root = 0)
+    uint32_t bound_depth = 0;      // deepest leaf of the bound bvh[] itself (what the reference's 16-entry stack has to cope with)
     uint32_t num_nodes() const { return (uint32_t)(nodes.size() / 16); }
     uint32_t num_slots() const { return (uint32_t)(tris.size() / 12); }
 };
