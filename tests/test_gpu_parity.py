@@ -253,6 +253,14 @@ def test_sharding_properties(gpu_doge):
     a = gpu_doge.render(CAM, sample_begin=0, sample_count=4, **kw)["accumf"]
     b = gpu_doge.render(CAM, sample_begin=4, sample_count=4, **kw)["accumf"]
     assert np.allclose(a + b, full, rtol=1e-6, atol=1e-6)
+    # the same for a shallow 1-spp frame, which the library renders with the one-launch kernel
+    one = dict(kw, max_bounces=2)
+    full1 = gpu_doge.render(CAM, sample_count=1, **one)
+    assert full1["counters"].launches == 1
+    parts1 = [gpu_doge.render(CAM, sample_count=1, tile_rank=r, tile_count=3, **one)["accumf"] for r in range(3)]
+    assert same_bits(sum(parts1), full1["accumf"])
+    deep1 = gpu_doge.render(CAM, sample_count=1, **dict(kw, max_bounces=8))      # deep paths: the wavefront pipeline
+    assert deep1["counters"].launches > 1
     # resume: continuing on top of a reloaded accumulation equals the uninterrupted render bit-for-bit
     gpu_doge.material.clearAccum()
     gpu_doge.material.writeAccumF32(a)
