@@ -44,6 +44,20 @@ __device__ __forceinline__ uint32_t wf_append_slot(unsigned int* counter, bool w
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + __popc(m & ((1u << lane) - 1u));
 }
+// The same in two halves, so that the atomic's round trip to L2 (the longest single wait of the shade kernel: 22 % of its
+// stall samples sat on the shuffle that broadcasts the result, ncu r01_v10) overlaps the arithmetic between them.
+__device__ __forceinline__ unsigned wf_append_begin(unsigned int* counter, bool want, unsigned& m) {
+    m = __ballot_sync(0xffffffffu, want);
+    unsigned base = 0u;
+    if (m != 0u && (int)(threadIdx.x & 31u) == __ffs(m) - 1) base = atomicAdd(counter, (unsigned)__popc(m));
+    return base;   // valid in the leader lane only, and only once the atomic has returned
+}
+__device__ __forceinline__ uint32_t wf_append_end(unsigned base, unsigned m) {
+    if (m == 0u) return 0u;
+    const unsigned lane = threadIdx.x & 31u;
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
 
 // Path id of a batch -> its pixel and sample (consecutive ids = the samples of one pixel).  False for pixels outside the
 // covered extent (ragged edge tiles).
@@ -209,14 +223,14 @@ __global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __
     float4* __restrict__ next = w.q[b.cur ^ 1u];
     for (uint32_t base = blockIdx.x * 256u; base < count; base += gridDim.x * 256u) {   // base is warp-uniform
         const uint32_t i = base + threadIdx.x;
-        bool cont = false;
-        float4 q0, q1, q2;
-        uint32_t x = 0, y = 0, k = 0;
+        bool cont = false, hit = false;
+        float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+        uint32_t x = 0, y = 0, k = 0, path = 0, rng = 0, pix = 0;
+        Ray cur; cur.o = cur.d = f3(0, 0, 0);
+        float3 thr = f3(0, 0, 0);
+        Hit rec;
         const bool live = i < count && (!PRIMARY || wf_path_pixel(a, b, i, x, y, k));
         if (live) {
-            Ray cur;
-            float3 thr;
-            uint32_t path, rng;
             if (PRIMARY) {
                 path = i;
                 wf_primary(a, x, y, k, cur, rng);
@@ -232,15 +246,24 @@ __global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __
             const uint2 h = stream_ld(w.hit + i);
             TravState t;
             t.closest = u2f(h.x); t.best = (int32_t)h.y;
-            Hit rec;
-            const bool hit = trav_finish(t, s, cur, rec);
-            const uint32_t pix = y * a.W + x;
+            hit = trav_finish(t, s, cur, rec);
+            pix = y * a.W + x;
             if (b.bounce == 0 && k == 0 && (a.flags & VCRT_FLAG_WRITE_AOV)) {
                 vcrt_aov o;
                 if (hit) { o.triangle = rec.triangle; o.material = (int32_t)rec.materialIndex; o.t = rec.t; o.backFace = (uint32_t)rec.backFaceInt; }
                 else { o.triangle = -1; o.material = -1; o.t = 0.0f; o.backFace = 0u; }
                 a.aov[pix] = o;
             }
+            if (hit) {   // whether the path goes on depends on the material type alone (scatter returns type == LIGHT)
+                uint32_t type; float3 unused;
+                load_mat(s, rec.materialIndex, type, unused);
+                cont = type != VCRT_MAT_LIGHT && (b.bounce + 1u) < a.env.max_bounces;
+            }
+        }
+        // reserve the slots of the next queue now; the answer is needed only for the stores at the end
+        unsigned am;
+        const unsigned abase = wf_append_begin(w.counts + (b.cur ^ 1u), cont, am);
+        if (live) {
             if (hit) {
                 Rng g;
                 g.pcg = rng;
@@ -248,9 +271,8 @@ __global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __
                 rng_begin_bounce<RNG_MODE>(g, b.bounce);
                 float3 albedo;
                 Ray nx;
-                const bool emits = scatter<SHADER, RNG_MODE, TRIG>(s, a.env, cur, rec, albedo, nx, g);
+                scatter<SHADER, RNG_MODE, TRIG>(s, a.env, cur, rec, albedo, nx, g);
                 thr = mul(thr, albedo);
-                cont = !emits && (b.bounce + 1u) < a.env.max_bounces;
                 q0 = make_float4(nx.o.x, nx.o.y, nx.o.z, q0.w);
                 q1 = make_float4(nx.d.x, nx.d.y, nx.d.z, u2f(g.pcg));
                 q2 = make_float4(thr.x, thr.y, thr.z, 0.0f);
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __
             }
             if (!cont) stream_st(w.sample_color + path, make_float4(thr.x, thr.y, thr.z, 1.0f));
         }
-        const uint32_t slot = wf_append_slot(w.counts + (b.cur ^ 1u), cont);
+        const uint32_t slot = wf_append_end(abase, am);
         if (cont) {
             float4* q = next + 3 * (size_t)slot;
             stream_st(q, q0); stream_st(q + 1, q1); stream_st(q + 2, q2);
