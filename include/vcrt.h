@@ -90,13 +90,19 @@ typedef struct {
 typedef struct { int32_t triangle; int32_t material; float t; uint32_t backFace; } vcrt_aov; /* triangle = -1 on a miss */
 
 typedef struct {
-    uint64_t rays;           /* closest-hit queries (primary + bounce) since the last reset */
+    uint64_t rays;           /* closest-hit queries (primary + bounce) answered since the last reset: what the shader's ray_color
+                                asks for, one per sample and bounce (ray-trace-compute.comp:321-323) */
     uint64_t nodes;          /* BVH node records fetched   (only with VCRT_FLAG_COUNT_TRAVERSAL) */
     uint64_t triangles;      /* triangle records fetched   (only with VCRT_FLAG_COUNT_TRAVERSAL) */
     double   kernel_ms;      /* device time of the render kernels (CUDA events) since the last reset */
     uint64_t launches;       /* kernels launched since the last reset */
     double   trace_ms;       /* device time of the dominant kernel alone (wavefront trace launches; CUDA events per launch) */
     uint64_t trace_launches; /* number of those launches */
+    uint64_t traversals;     /* BVH traversals actually run.  The wavefront pipeline traces bounce 0 once per pixel and shares the hit
+                                among the pixel's samples (the shader's primary ray does not depend on the sample, :352-373), so
+                                traversals = rays - primary_rays * (1 - 1/sample_count) there; every other kernel: = rays */
+    uint64_t primary_rays;   /* the bounce-0 part of `rays` */
+    double   primary_trace_ms; /* the part of trace_ms spent in bounce-0 launches */
 } vcrt_counters;
 
 enum { VCRT_OK = 0, VCRT_ERR_INVALID = -1, VCRT_ERR_CUDA = -2, VCRT_ERR_STATE = -3, VCRT_ERR_NOMEM = -4 };
@@ -170,7 +176,10 @@ int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile
  * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "dispatch_traversal": what vcrt_dispatch walks -- "auto" (default: the fast tree whenever
  * the bound tree is at most 13 levels deep, i.e. whenever the shader's 16-entry stack cannot overflow; identical frames), "reference" (always the
  * literal hit_bvh), "fast"; "wf_batch_paths":
- * paths per wavefront batch (queue memory: 120 B per path); "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
+ *  paths per wavefront batch (queue memory: 120 B per path); "wf_streams": "auto" (default) or 1..4 -- a wavefront render
+ * whose work fits several batches runs them as parallel pipelines on that many streams (auto: 4 for renders of 256 Ki..32 Mi paths,
+ * e.g. a 1-spp frame, else 1); "trace_timing": "on" (default) | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
+ * "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 
 /* Read-only facts about ctx as text: "fast_nodes" -> "q15x4" | "q15" | "f32" | "none" (what the fast traversal walks after the last

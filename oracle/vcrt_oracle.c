@@ -121,6 +121,7 @@ static inline float rng_next(rng_t* g) {
 typedef struct {
     const vcrt_oracle_scene* s;
     uint32_t lights_length, stack_depth, max_bounces, shader, traversal, trig;
+    uint32_t ubo_num_triangles;   /* ubo.numTriangles: loop bound of hit_scene (:229) */
     int count;
 } env_t;
 
@@ -195,8 +196,9 @@ static int hit_scene(const env_t* e, const ray_t* r, hit_t* rec) {
     hit_t tmp;
     int hit_anything = 0;
     float closest = t_max;
-    for (uint32_t i = 0; i < e->s->num_triangles; ++i)
+    for (uint32_t i = 0; i < e->ubo_num_triangles; ++i)   /* :229 -- ubo.numTriangles, reads past the buffer return the zero triangle */
         if (hit_triangle(e, (int)i, r, t_min, closest, &tmp)) { hit_anything = 1; closest = tmp.t; *rec = tmp; }
+    if (e->shader == VCRT_SHADER_SIMPLE) return hit_anything;   /* ray-trace-compute-simple.comp:106-123 has no sphere loop */
     closest = t_max;
     for (uint32_t j = 0; j < e->s->num_spheres; ++j)
         if (hit_sphere(e, (int)j, r, t_min, closest, &tmp)) { hit_anything = 1; closest = tmp.t; *rec = tmp; }
@@ -382,6 +384,7 @@ int vcrt_oracle_render(const vcrt_oracle_scene* scene, const vcrt_ubo* ubo, cons
     if (e.stack_depth > ORACLE_MAX_STACK) return VCRT_ERR_INVALID;
     e.lights_length = prm->lights_length ? prm->lights_length : scene->num_lights;
     e.count = (prm->flags & VCRT_FLAG_COUNT_TRAVERSAL) != 0;
+    e.ubo_num_triangles = ubo->numTriangles;
     const uint32_t spp = prm->sample_count ? prm->sample_count : 1u;
     const uint32_t tilesX = (W + 31) / 32;
     const uint32_t covW = (prm->flags & VCRT_FLAG_REF_DISPATCH_COVERAGE) ? (W / 32) * 32 : W;

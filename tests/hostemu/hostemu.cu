@@ -19,7 +19,7 @@ static void run(const KernelArgs& a, unsigned long long* counters) {
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : rays, nodes, tris)
     for (uint32_t item = 0; item < items; ++item) {
         uint32_t x, y;
-        TraceStats st = {0u, 0u, 0u};
+        TraceStats st = {0u, 0u, 0u, 0u};
         if (item_to_pixel(a, item, x, y)) render_pixel<SHADER, TRAV, RNG_MODE, TRIG, true>(a, x, y, st);
         rays += st.rays; nodes += st.nodes; tris += st.tris;
     }
@@ -49,7 +49,7 @@ extern "C" int hostemu_render(const void* tris, uint32_t ntris, const void* mats
             if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
             return -1;
         }
-        if (!(p->_reserved & 1u) && !rebuild_fast_bvh_sah(fb, e)) {   // test hook: _reserved bit 0 keeps the bound topology
+        if ((!(p->_reserved & 1u) && !rebuild_fast_bvh_sah(fb, e)) || !check_fast_depth(fb, e)) {   // test hook: _reserved bit 0 keeps the bound topology
             if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
             return -1;
         }

@@ -71,6 +71,54 @@ def test_duplicate_triangles_tie_rule(oracle, hostemu):
     assert (a["aov"]["triangle"] >= 0).sum() > 1000
 
 
+def test_absent_child_slots_in_float_nodes(oracle, hostemu):
+    """The bound topology kept as it is (fast_bvh=topology) with 64-byte float nodes, on a tree whose inner nodes have one
+    child or a child with neither triangle nor children: an absent slot is the box (+inf, -inf), which a min/max slab test
+    reports as hit unless the verdict is gated on the child code (it used to end the ray's traversal early: wrong hits)."""
+    import tinybvh
+    for seed, n in ((31, 7), (32, 64), (33, 900)):
+        sc = dict(small_scene(n_tris=n, seed=seed))
+        nodes = tinybvh.add_degenerate_inner_nodes(sc["bvh"].view(tinybvh.NODE))
+        sc["bvh"] = nodes.view(np.uint8).reshape(-1).copy()
+        kw = dict(shader="full", max_bounces=5, sample_count=2, accum="f32", rng="philox", stack_depth=64)
+        a = oracle.render(sc, (0.0, 6.0, 1.5), 96, 64, make_params(traversal="reference", **kw), want_aov=True)
+        for reserved in (3, 1, 9, 0):   # topology + f32 | topology + q15 | topology + q15x4 | SAH rebuild + q15
+            p = make_params(traversal="fast", **kw)
+            p._reserved = reserved
+            b = hostemu.render(sc, (0.0, 6.0, 1.5), 96, 64, p, want_aov=True)
+            assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (seed, n, reserved)
+        assert (a["aov"]["triangle"] >= 0).sum() > 100
+
+
+def test_deep_bound_tree_is_fine_once_rebuilt(oracle, hostemu):
+    """A degenerate (list-shaped) bound tree, deeper than the fast traversal's stack: keeping its topology is refused, the
+    SAH rebuild (the default) walks its own shallow tree and reproduces the reference traversal's hits."""
+    import tinybvh
+    sc = dict(small_scene(n_tris=46, seed=41))   # 50 triangles with the floor and the emitter: depth 49 > 45, reference stack 51 < 64
+    tri = sc["triangles"].view(tinybvh.TRI)
+    n = len(tri)
+    lo = np.minimum(np.minimum(tri["v0"], tri["v1"]), tri["v2"]) - np.float32(1e-4)
+    hi = np.maximum(np.maximum(tri["v0"], tri["v1"]), tri["v2"]) + np.float32(1e-4)
+    nodes = np.zeros(2 * n - 1, tinybvh.NODE)
+    nodes["left"] = nodes["right"] = nodes["object"] = -1
+    for i in range(n - 1):          # inner node 2i: {leaf 2i+1, rest 2i+2}
+        nodes[2 * i]["left"], nodes[2 * i]["right"] = 2 * i + 1, 2 * i + 2
+        nodes[2 * i]["min"], nodes[2 * i]["max"] = lo[i:].min(axis=0), hi[i:].max(axis=0)
+        nodes[2 * i + 1]["object"] = i
+        nodes[2 * i + 1]["min"], nodes[2 * i + 1]["max"] = lo[i], hi[i]
+    nodes[2 * n - 2]["object"] = n - 1
+    nodes[2 * n - 2]["min"], nodes[2 * n - 2]["max"] = lo[n - 1], hi[n - 1]
+    sc["bvh"] = nodes.view(np.uint8).reshape(-1).copy()
+    kw = dict(shader="full", max_bounces=3, sample_count=1, accum="f32", stack_depth=64)
+    a = oracle.render(sc, (0.0, 6.0, 1.5), 64, 48, make_params(traversal="reference", **kw), want_aov=True)
+    b = hostemu.render(sc, (0.0, 6.0, 1.5), 64, 48, make_params(traversal="fast", **kw), want_aov=True)
+    assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"])
+    p = make_params(traversal="fast", **kw)
+    p._reserved = 1
+    with pytest.raises(RuntimeError, match="exceeds the fast traversal stack"):
+        hostemu.render(sc, (0.0, 6.0, 1.5), 64, 48, p)
+
+
 def test_brute_force_with_spheres(oracle, hostemu):
     sc = small_scene(n_tris=30, seed=4)
     kw = dict(shader="full", traversal="brute_force", max_bounces=4, sample_count=2)

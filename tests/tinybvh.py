@@ -68,3 +68,39 @@ def build_scene(n_tris=64, seed=7, glass=True, metal=True, extent=1.0):
     return {"triangles": tris.view(np.uint8).reshape(-1).copy(), "materials": mats.view(np.uint8).reshape(-1).copy(),
             "bvh": nodes.view(np.uint8).reshape(-1).copy(), "lights": lights.view(np.uint8).reshape(-1).copy(),
             "spheres": spheres.view(np.uint8).reshape(-1).copy()}
+
+
+def add_degenerate_inner_nodes(nodes, every=3):
+    """Returns a tree with the same leaves in the same visiting order, where every `every`-th leaf is wrapped in an inner node
+    that has ONE child (the leaf, on alternating sides) and every other `every`-th one gets a sibling with neither a triangle
+    nor children.  The reference shader walks such trees without noticing (-1 children are skipped,
+    ray-trace-compute.comp:279-281; a node without an object only forwards its children, :290-306); a repacked traversal
+    has to represent the absent slots explicitly."""
+    nodes = nodes.copy()
+    extra = []
+    base = len(nodes)
+    k = 0
+    for i in range(base):
+        if nodes[i]["object"] < 0:
+            continue
+        k += 1
+        if k % every == 0:          # leaf i becomes an inner node with one child: the leaf, moved to a new slot
+            leaf = nodes[i].copy()
+            idx = base + len(extra)
+            extra.append(leaf)
+            nodes[i]["object"] = -1
+            if (k // every) % 2:
+                nodes[i]["left"], nodes[i]["right"] = idx, -1
+            else:
+                nodes[i]["left"], nodes[i]["right"] = -1, idx
+        elif k % every == 1:        # leaf i becomes an inner node {leaf, childless node}
+            leaf = nodes[i].copy()
+            hollow = nodes[i].copy()
+            hollow["object"] = -1
+            idx = base + len(extra)
+            extra.extend([leaf, hollow])
+            nodes[i]["object"] = -1
+            nodes[i]["left"], nodes[i]["right"] = idx, idx + 1
+    if extra:
+        nodes = np.concatenate([nodes, np.array(extra, NODE)])
+    return nodes

@@ -27,7 +27,8 @@ class RenderParams(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("nodes", C.c_uint64), ("triangles", C.c_uint64), ("kernel_ms", C.c_double),
-                ("launches", C.c_uint64), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64)]
+                ("launches", C.c_uint64), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("traversals", C.c_uint64),
+                ("primary_rays", C.c_uint64), ("primary_trace_ms", C.c_double)]
 
 
 assert C.sizeof(Ubo) == 32 and C.sizeof(RenderParams) == 64

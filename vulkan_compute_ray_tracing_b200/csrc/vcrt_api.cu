@@ -47,8 +47,13 @@ struct vcrt_ctx {
     bool fast_ok = false;
     std::string fast_err;
     DevBuf fnodes, ftris;
-    DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues
-    uint32_t wf_capacity = 0;
+    DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues (all pipelines' sets, back to back)
+    uint32_t wf_capacity = 0;              // paths per queue set
+    int wf_sets = 0;                       // queue sets the buffers are currently carved into
+    int wf_streams = 0;                    // option "wf_streams": 0 "auto" | 1..VCRT_MAX_PIPES pipelines of a wavefront render
+    cudaStream_t pipe_stream[VCRT_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (the render stream)
+    cudaEvent_t fork_ev = nullptr, join_ev[VCRT_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;      // timing events of finished renders, reused
     uint32_t wf_batch = 256u << 20;        // option "wf_batch_paths": paths per wavefront batch (queue memory = 120 B per path, allocated for what a call needs).
                                            // Every trace launch ends in a ~110 us tail (the longest rays): C3 at 64 spp, 32 Mi / 64 Mi / one batch: 5395 / 5620 / 5763 Mrays/s
     int32_t froot = (int32_t)0x80000000;
@@ -56,7 +61,7 @@ struct vcrt_ctx {
     uint32_t W = 0, H = 0;
     DevBuf target, accum8, accumf, aov, present;
     vcrt_ubo ubo;
-    unsigned long long* d_counters = nullptr;   // rays, nodes, tris, work counter
+    unsigned long long* d_counters = nullptr;   // [0] queries [1] nodes [2] tris [3] work counter [4] traversals [5] bounce-0 queries (vcrt_kernels.inl: flush_stats)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     double kernel_ms = 0.0;
     uint64_t launches = 0;
@@ -114,8 +119,8 @@ int vcrt_create(int device, vcrt_ctx** out) {
     c->device = device;
     std::memset(&c->ubo, 0, sizeof c->ubo);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream)) != cudaSuccess) {
+        (e = cudaMalloc((void**)&c->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "create context");
         delete c;
         return rc;
@@ -156,6 +161,17 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         const long long n = atoll(value);
         if (n < 1024 || n > (1ll << 30)) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: wf_batch_paths must be 1024..2^30");
         c->wf_batch = (uint32_t)n;
+        return VCRT_OK;
+    }
+    if (k == "wf_streams") {
+        const int n = v == "auto" ? 0 : atoi(value);
+        if (n < 0 || n > VCRT_MAX_PIPES || (n == 0 && v != "auto")) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: wf_streams must be 'auto' or 1..4");
+        c->wf_streams = n;
+        return VCRT_OK;
+    }
+    if (k == "trace_timing") {
+        if (v != "on" && v != "off") return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: trace_timing must be 'on' or 'off'");
+        c->trace_timer.enabled = v == "on";
         return VCRT_OK;
     }
     if (k == "leaf_threshold" || k == "shade_threshold" || k == "continue_threshold") {
@@ -201,6 +217,12 @@ int vcrt_destroy(vcrt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
+    for (int i = 1; i < VCRT_MAX_PIPES; ++i) {
+        if (c->pipe_stream[i]) { cudaStreamSynchronize(c->pipe_stream[i]); cudaStreamDestroy(c->pipe_stream[i]); }
+        if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
+    }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     c->trace_timer.destroy();
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
     for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes, &c->q4nodes, &c->present}) if (b->ptr) cudaFree(b->ptr);
@@ -287,8 +309,8 @@ static void harvest_events(vcrt_ctx* c) {
     while (done < c->events.size() && cudaEventQuery(c->events[done].second) == cudaSuccess) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, c->events[done].first, c->events[done].second) == cudaSuccess) c->kernel_ms += ms;
-        cudaEventDestroy(c->events[done].first);
-        cudaEventDestroy(c->events[done].second);
+        c->ev_pool.push_back(c->events[done].first);
+        c->ev_pool.push_back(c->events[done].second);
         ++done;
     }
     c->events.erase(c->events.begin(), c->events.begin() + (long)done);
@@ -297,40 +319,43 @@ static void harvest_events(vcrt_ctx* c) {
 
 static int prepare_fast(vcrt_ctx* c) {
     if (c->fast_dirty) {
+        // The context counts as prepared only once every record is on the device: any early return below leaves it dirty, so the
+        // next render retries (or fails again) instead of launching with missing or stale node / triangle buffers.
+        c->fast_ok = false;
         FastBvh fb;
         c->fast_err.clear();
-        c->fast_ok = build_fast_bvh((const vcrt_bvh_node*)c->host_bvh.data(), (uint32_t)(c->host_bvh.size() / sizeof(vcrt_bvh_node)),
-                                    (const vcrt_triangle*)c->host_tris.data(), (uint32_t)(c->host_tris.size() / sizeof(vcrt_triangle)), fb, c->fast_err);
-        if (c->fast_ok && c->fast_sah) c->fast_ok = rebuild_fast_bvh_sah(fb, c->fast_err);
-        if (c->fast_ok) precompute_triangles(fb);
-        c->fast_dirty = false;
-        if (c->fast_ok) {
-            int rc;
-            if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris64.size() * 4, "allocate repacked triangles"))) return rc;
-            if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
-            if (!fb.tris64.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris64.data(), fb.tris64.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
-            // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
-            c->quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, (c->fast_nodes == 1 || c->fast_nodes == 3) ? 3.0e38f : 2.5e-4f);
-            // 4-wide form of the quantised tree for the wavefront trace kernel ("auto" and "q15x4"; "q15" keeps the binary tree)
-            c->wide = c->quantized && c->fast_nodes != 1 && build_wide_bvh(fb, VCRT_FAST_STACK);
-            if (c->wide) {
-                if ((rc = ensure(c, c->q4nodes, fb.q4nodes.size() * 4, "allocate 4-wide nodes"))) return rc;
-                CU(c, cudaMemcpyAsync(c->q4nodes.ptr, fb.q4nodes.data(), fb.q4nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload 4-wide nodes");
-                c->froot4 = fb.root4;
-                c->nf4nodes = (uint32_t)(fb.q4nodes.size() / 16);
-            }
-            if (c->quantized) {
-                if ((rc = ensure(c, c->qnodes, fb.qnodes.size() * 4, "allocate quantised nodes"))) return rc;
-                CU(c, cudaMemcpyAsync(c->qnodes.ptr, fb.qnodes.data(), fb.qnodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload quantised nodes");
-                std::memcpy(c->qorg, fb.qorg, sizeof c->qorg);
-                std::memcpy(c->qext, fb.qext, sizeof c->qext);
-            }
-            CU(c, cudaStreamSynchronize(c->stream), "synchronize");
-            c->froot = fb.root;
-            c->nfnodes = fb.num_nodes();
-            c->fast_depth = fb.depth;
-            c->bound_depth = fb.bound_depth;
+        bool ok = build_fast_bvh((const vcrt_bvh_node*)c->host_bvh.data(), (uint32_t)(c->host_bvh.size() / sizeof(vcrt_bvh_node)),
+                                 (const vcrt_triangle*)c->host_tris.data(), (uint32_t)(c->host_tris.size() / sizeof(vcrt_triangle)), fb, c->fast_err);
+        if (ok && c->fast_sah) ok = rebuild_fast_bvh_sah(fb, c->fast_err);
+        if (ok) ok = check_fast_depth(fb, c->fast_err);   // the tree that will be walked: a deep bound tree is fine once rebuilt
+        if (!ok) { c->fast_dirty = false; return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err); }   // a property of the bound tree: no retry
+        precompute_triangles(fb);
+        int rc;
+        if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris64.size() * 4, "allocate repacked triangles"))) return rc;
+        if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
+        if (!fb.tris64.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris64.data(), fb.tris64.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
+        // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
+        const bool quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, (c->fast_nodes == 1 || c->fast_nodes == 3) ? 3.0e38f : 2.5e-4f);
+        // 4-wide form of the quantised tree for the wavefront trace kernel ("auto" and "q15x4"; "q15" keeps the binary tree)
+        const bool wide = quantized && c->fast_nodes != 1 && build_wide_bvh(fb, VCRT_FAST_STACK);
+        if (wide) {
+            if ((rc = ensure(c, c->q4nodes, fb.q4nodes.size() * 4, "allocate 4-wide nodes"))) return rc;
+            CU(c, cudaMemcpyAsync(c->q4nodes.ptr, fb.q4nodes.data(), fb.q4nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload 4-wide nodes");
         }
+        if (quantized) {
+            if ((rc = ensure(c, c->qnodes, fb.qnodes.size() * 4, "allocate quantised nodes"))) return rc;
+            CU(c, cudaMemcpyAsync(c->qnodes.ptr, fb.qnodes.data(), fb.qnodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload quantised nodes");
+        }
+        CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+        c->quantized = quantized; c->wide = wide;
+        if (wide) { c->froot4 = fb.root4; c->nf4nodes = (uint32_t)(fb.q4nodes.size() / 16); }
+        if (quantized) { std::memcpy(c->qorg, fb.qorg, sizeof c->qorg); std::memcpy(c->qext, fb.qext, sizeof c->qext); }
+        c->froot = fb.root;
+        c->nfnodes = fb.num_nodes();
+        c->fast_depth = fb.depth;
+        c->bound_depth = fb.bound_depth;
+        c->fast_ok = true;
+        c->fast_dirty = false;
     }
     if (!c->fast_ok) return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err);
     return VCRT_OK;
@@ -373,13 +398,19 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     a.work_counter = (unsigned int*)(c->d_counters + 3);
     a.leaf_threshold = c->leaf_threshold; a.shade_threshold = c->shade_threshold; a.continue_threshold = c->continue_threshold;
 
-    cudaEvent_t e0, e1;
-    CU(c, cudaEventCreate(&e0), "create event");
-    CU(c, cudaEventCreate(&e1), "create event");
-    CU(c, cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream), "reset work counter");
-    CU(c, cudaEventRecord(e0, c->stream), "record event");
-    const bool count = (p.flags & VCRT_FLAG_COUNT_TRAVERSAL) != 0;
+    // timing events come from a pool (a frame loop renders thousands of frames: no event creation in steady state)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    for (cudaEvent_t* ev : {&e0, &e1}) {
+        if (!c->ev_pool.empty()) { *ev = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else CU(c, cudaEventCreate(ev), "create event");
+    }
+    auto give_back = [&]() { c->ev_pool.push_back(e0); c->ev_pool.push_back(e1); };
     cudaError_t e;
+    if ((e = cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream)) != cudaSuccess || (e = cudaEventRecord(e0, c->stream)) != cudaSuccess) {
+        give_back();
+        return cuda_fail(c, e, "start render");
+    }
+    const bool count = (p.flags & VCRT_FLAG_COUNT_TRAVERSAL) != 0;
     uint32_t nlaunch = 1;
     // A 1-spp frame of a shallow shader (the reference's own frame: NUM_BOUNCES 2 or 4) is one launch of the one-thread-per-pixel
     // kernel instead of three launches per bounce of the wavefront pipeline: 0.09 instead of 0.59 ms at 800x600 on the bundled
@@ -387,27 +418,51 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     bool one_launch = (p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL)) != 0;
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && a.sample_count == 1u && a.env.max_bounces <= 4u) { a.flags |= VCRT_FLAG_STATIC_KERNEL; one_launch = true; }
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch) {
-        // wavefront pipeline: queues sized for a batch of paths (a range of pixels x all samples of the call)
-        // batch = as many whole pixels (all samples of the call) as fit wf_batch paths, but no more than the call needs
+        // wavefront pipeline: a batch = a range of pixels x all samples of the call; queues sized for what the call needs, at most
+        // wf_batch paths per batch.  Small renders (a 1-spp frame) are cut into up to four batches that run as parallel pipelines on
+        // their own streams, so that the tails of their trace launches overlap (option "wf_streams").
         const uint64_t need = (uint64_t)a.owned_tiles * 1024u * a.sample_count;
-        uint32_t want = (uint32_t)(need < c->wf_batch ? need : c->wf_batch);
+        int sets = c->wf_streams ? c->wf_streams : (need <= (32ull << 20) && need >= (256ull << 10) ? VCRT_MAX_PIPES : 1);
+        uint64_t per_set = (need + (uint64_t)sets - 1) / (uint64_t)sets;
+        per_set = (per_set + a.sample_count - 1) / a.sample_count * a.sample_count;   // whole pixels
+        if (per_set > c->wf_batch) per_set = c->wf_batch;
+        uint32_t want = (uint32_t)per_set;
         if (want < a.sample_count) want = a.sample_count;
         if (want < 1024u) want = 1024u;
-        if (c->wf_capacity != want) {
-            int rc;
-            if ((rc = ensure(c, c->wf_q0, (size_t)want * 48, "allocate ray queue")) || (rc = ensure(c, c->wf_q1, (size_t)want * 48, "allocate ray queue")) ||
-                (rc = ensure(c, c->wf_hit, (size_t)want * 8, "allocate hit buffer")) || (rc = ensure(c, c->wf_color, (size_t)want * 16, "allocate sample buffer")) ||
-                (rc = ensure(c, c->wf_counts, 16, "allocate queue counters"))) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
-            c->wf_capacity = want;
+        int rc = VCRT_OK;
+        if (c->wf_capacity != want || c->wf_sets != sets) {
+            const size_t n = (size_t)want * (size_t)sets;
+            if ((rc = ensure(c, c->wf_q0, n * 48, "allocate ray queue")) || (rc = ensure(c, c->wf_q1, n * 48, "allocate ray queue")) ||
+                (rc = ensure(c, c->wf_hit, n * 8, "allocate hit buffer")) || (rc = ensure(c, c->wf_color, n * 16, "allocate sample buffer")) ||
+                (rc = ensure(c, c->wf_counts, 64 * VCRT_MAX_PIPES, "allocate queue counters"))) { give_back(); return rc; }
+            c->wf_capacity = want; c->wf_sets = sets;
         }
+        WfPipes pipes;
+        std::memset(&pipes, 0, sizeof pipes);
+        pipes.n = sets;
+        pipes.stream[0] = c->stream;
+        for (int i = 0; i < sets; ++i) {
+            if (i > 0) {
+                if (!c->pipe_stream[i] && (e = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create pipeline stream"); }
+                if (!c->join_ev[i] && (e = cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create event"); }
+                pipes.stream[i] = c->pipe_stream[i];
+                pipes.join[i] = c->join_ev[i];
+            }
+            WfQueues& q = pipes.q[i];
+            q.q[0] = (float4*)c->wf_q0.ptr + (size_t)i * want * 3; q.q[1] = (float4*)c->wf_q1.ptr + (size_t)i * want * 3;
+            q.hit = (uint2*)c->wf_hit.ptr + (size_t)i * want; q.sample_color = (float4*)c->wf_color.ptr + (size_t)i * want;
+            q.counts = (unsigned int*)c->wf_counts.ptr + 16 * i;
+            q.capacity = want;
+        }
+        if (sets > 1 && !c->fork_ev && (e = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create event"); }
+        pipes.fork = c->fork_ev;
         nlaunch = 0;
-        e = launch_render_wavefront(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream, (float4*)c->wf_q0.ptr, (float4*)c->wf_q1.ptr,
-                                    (uint2*)c->wf_hit.ptr, (float4*)c->wf_color.ptr, (unsigned int*)c->wf_counts.ptr, c->wf_capacity, &nlaunch, &c->trace_timer);
+        e = launch_render_wavefront(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, pipes, &nlaunch, &c->trace_timer);
     } else if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     else if (p.traversal == VCRT_TRAVERSAL_BRUTE_FORCE) e = launch_render_brute(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
     else e = launch_render_reference(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
-    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, e, "launch render kernel"); }
-    CU(c, cudaEventRecord(e1, c->stream), "record event");
+    if (e != cudaSuccess) { give_back(); return cuda_fail(c, e, "launch render kernel"); }
+    if ((e = cudaEventRecord(e1, c->stream)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "record event"); }
     c->events.emplace_back(e0, e1);
     c->launches += nlaunch;
     if (c->events.size() >= 256 || c->trace_timer.pending.size() >= 2048) harvest_events(c);   // a frame loop that never asks for counters
@@ -549,8 +604,8 @@ static int drain_events(vcrt_ctx* c) {
     for (auto& ev : c->events) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) c->kernel_ms += ms;
-        cudaEventDestroy(ev.first);
-        cudaEventDestroy(ev.second);
+        c->ev_pool.push_back(ev.first);
+        c->ev_pool.push_back(ev.second);
     }
     c->events.clear();
     c->trace_timer.drain(&c->trace_ms, &c->trace_launches);
@@ -562,13 +617,16 @@ int vcrt_get_counters(vcrt_ctx* c, vcrt_counters* out) {
     CU(c, cudaSetDevice(c->device), "set device");
     int rc = drain_events(c);
     if (rc) return rc;
-    unsigned long long h[3];
+    unsigned long long h[6];
     CU(c, cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost), "read counters");
     out->rays = h[0]; out->nodes = h[1]; out->triangles = h[2];
     out->kernel_ms = c->kernel_ms;
     out->launches = c->launches;
     out->trace_ms = c->trace_ms;
     out->trace_launches = c->trace_launches;
+    out->traversals = h[4];
+    out->primary_rays = h[5];
+    out->primary_trace_ms = c->trace_timer.primary_ms;
     return VCRT_OK;
 }
 
@@ -577,7 +635,8 @@ int vcrt_reset_counters(vcrt_ctx* c) {
     CU(c, cudaSetDevice(c->device), "set device");
     int rc = drain_events(c);
     if (rc) return rc;
-    CU(c, cudaMemset(c->d_counters, 0, 3 * sizeof(unsigned long long)), "reset counters");
+    CU(c, cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)), "reset counters");
+    c->trace_timer.primary_ms = 0.0;
     c->kernel_ms = 0.0;
     c->launches = 0;
     c->trace_ms = 0.0;

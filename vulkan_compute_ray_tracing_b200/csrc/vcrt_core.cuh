@@ -257,7 +257,7 @@ struct SceneView {
 struct Ray { float3 o, d; };
 struct Hit { float3 p, normal; uint32_t materialIndex; float t; int backFaceInt; int triangle; };
 
-struct TraceStats { uint32_t rays, nodes, tris; };
+struct TraceStats { uint32_t rays, nodes, tris, prim; };   // prim: bounce-0 rays among `rays`
 
 // Out-of-range reads return zero (robustBufferAccess), like oracle/_ref's Ssbo::operator[].
 VCRT_HD void load_tri(const SceneView& s, uint32_t i, float3& v0, float3& v1, float3& v2, uint32_t& mat) {
@@ -349,12 +349,15 @@ VCRT_HD bool hit_sphere(const SceneView& s, uint32_t si, const Ray& r, float tMi
 #define VCRT_T_MIN 0.001f
 #define VCRT_T_MAX 10000.0f
 
-// hit_scene, ray-trace-compute.comp:222-247 (brute force; the sphere loop restarts from t_max)
-VCRT_HD bool hit_scene(const SceneView& s, const Ray& r, Hit& rec, TraceStats& st) {
+// hit_scene, ray-trace-compute.comp:222-247 (brute force; the sphere loop restarts from t_max).  The triangle loop runs to
+// ubo.numTriangles (:229), not to the buffer length: reads past the bound buffer return the zero triangle (never hit).
+// The simple shader's hit_scene (ray-trace-compute-simple.comp:106-123) has no sphere loop.
+template <int SHADER>
+VCRT_HD bool hit_scene(const SceneView& s, uint32_t num_triangles, const Ray& r, Hit& rec, TraceStats& st) {
     bool any = false;
     float closest = VCRT_T_MAX;
     int best = -1;
-    for (uint32_t i = 0; i < s.ntris; ++i) {
+    for (uint32_t i = 0; i < num_triangles; ++i) {
         float3 v0, v1, v2; uint32_t mat; float t;
         load_tri(s, i, v0, v1, v2, mat);
         st.tris++;
@@ -365,6 +368,7 @@ VCRT_HD bool hit_scene(const SceneView& s, const Ray& r, Hit& rec, TraceStats& s
         load_tri(s, (uint32_t)best, v0, v1, v2, mat);
         finish_triangle_hit(v0, v1, v2, mat, best, r, closest, rec);
     }
+    if (SHADER == VCRT_SHADER_SIMPLE) return any;
     closest = VCRT_T_MAX;
     for (uint32_t j = 0; j < s.nspheres; ++j) {
         Hit tmp;

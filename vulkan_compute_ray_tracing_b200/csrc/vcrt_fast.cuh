@@ -107,8 +107,10 @@ VCRT_HD void trav_test_children(const TravState& t, const SceneView& s, float& l
     const float lF = fmin_(fmin_(fmax_(lx0, lx1), fmax_(ly0, ly1)), fmax_(lz0, lz1)) * 1.0000004f;
     rN = fmax_(fmax_(fmin_(rx0, rx1), fmin_(ry0, ry1)), fmax_(fmin_(rz0, rz1), 0.0f));
     const float rF = fmin_(fmin_(fmax_(rx0, rx1), fmax_(ry0, ry1)), fmax_(rz0, rz1)) * 1.0000004f;
-    hl = lN <= fmin_(lF, t.closest);
-    hr = rN <= fmin_(rF, t.closest);
+    // an absent child is stored as the box (+inf, -inf), which the min/max slab test above would report as entered at 0 and
+    // left at +inf: the verdict is gated on the child code (the quantised formats need no gate: their empty box is empty)
+    hl = cl != VCRT_FAST_EMPTY && lN <= fmin_(lF, t.closest);
+    hr = cr != VCRT_FAST_EMPTY && rN <= fmin_(rF, t.closest);
 }
 
 // ---- 4-wide nodes (vcrt_repack.h: build_wide_bvh): a node is two halves in the quantised binary format.

@@ -39,6 +39,7 @@ inline void setup_args(KernelArgs& a, const vcrt_ubo& ubo, const vcrt_render_par
     a.sample_begin = p.sample_begin;
     a.sample_count = p.sample_count ? p.sample_count : 1u;
     a.accum_mode = p.accum_mode; a.philox_seed = p.philox_seed; a.flags = p.flags;
+    a.num_triangles = ubo.numTriangles;
 }
 
 }  // namespace vcrt

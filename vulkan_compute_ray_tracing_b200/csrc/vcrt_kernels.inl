@@ -3,11 +3,15 @@
 // template instantiations of the three traversal modes compile in parallel.
 #include <cuda_runtime.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "vcrt_path.cuh"
 #include "vcrt_launch.h"
 
 namespace vcrt {
-__device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStats& st);
+__device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStats& st, uint32_t queries_per_ray = 1u, bool all_primary = false);
 }
 #if VCRT_TU_TRAV == 1
 #include "vcrt_persistent.cuh"
@@ -16,14 +20,19 @@ __device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStat
 
 namespace vcrt {
 
-__device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStats& st) {
+// counters: [0] closest-hit queries answered  [1] node records fetched  [2] triangle records fetched  [3] work counter of the
+// persistent kernels  [4] traversals run  [5] bounce-0 queries.  A traced ray answers `queries_per_ray` queries (the wavefront
+// pipeline traces bounce 0 once per pixel for all of its samples); `all_primary`: every ray of this launch is a primary ray.
+__device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStats& st, uint32_t queries_per_ray, bool all_primary) {
     unsigned rays = __reduce_add_sync(0xffffffffu, st.rays);
     unsigned nodes = __reduce_add_sync(0xffffffffu, st.nodes);
     unsigned tris = __reduce_add_sync(0xffffffffu, st.tris);
+    unsigned prim = __reduce_add_sync(0xffffffffu, all_primary ? st.rays : st.prim);
     if ((threadIdx.x & 31u) == 0u) {
-        if (rays) atomicAdd(a.counters + 0, (unsigned long long)rays);
+        if (rays) { atomicAdd(a.counters + 0, (unsigned long long)rays * queries_per_ray); atomicAdd(a.counters + 4, (unsigned long long)rays); }
         if (nodes) atomicAdd(a.counters + 1, (unsigned long long)nodes);
         if (tris) atomicAdd(a.counters + 2, (unsigned long long)tris);
+        if (prim) atomicAdd(a.counters + 5, (unsigned long long)prim * queries_per_ray);
     }
 }
 
@@ -32,11 +41,34 @@ __device__ __forceinline__ void flush_stats(const KernelArgs& a, const TraceStat
 template <int SHADER, int TRAV, int RNG_MODE, int TRIG, bool COUNT>
 __global__ void __launch_bounds__(VCRT_BLOCK) render_static_kernel(const __grid_constant__ KernelArgs a) {
     const uint32_t item = blockIdx.x * VCRT_BLOCK + threadIdx.x;
-    TraceStats st = {0u, 0u, 0u};
+    TraceStats st = {0u, 0u, 0u, 0u};
     uint32_t x, y;
     if (item < a.owned_tiles * 1024u && item_to_pixel(a, item, x, y))
         render_pixel<SHADER, TRAV, RNG_MODE, TRIG, COUNT>(a, x, y, st);
     flush_stats(a, st);
+}
+
+// Grid of a persistent kernel = one resident wave on the CURRENT device (SM count x resident blocks per SM), cached per
+// (device, kernel) behind a mutex: contexts on different devices -- and host threads driving different contexts -- are
+// independent (include/vcrt.h), so neither a process-wide static nor an unguarded one will do.  *sms_out: the SM count.
+static cudaError_t persistent_grid(const void* fn, int block, int* grid, int* sms_out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, std::pair<int, int>> cache;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, fn});
+    if (it == cache.end()) {
+        int sms = 0, per_sm = 0;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+            (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0)) != cudaSuccess)
+            return e;
+        it = cache.emplace(std::make_pair(dev, fn), std::make_pair(sms * (per_sm > 0 ? per_sm : 1), sms)).first;
+    }
+    *grid = it->second.first;
+    if (sms_out) *sms_out = it->second.second;
+    return cudaSuccess;
 }
 
 template <int SHADER, int RNG_MODE, int TRIG, bool COUNT>
@@ -46,15 +78,9 @@ static cudaError_t launch_one(const KernelArgs& a, cudaStream_t stream) {
 #if VCRT_TU_TRAV == 1
     if (!(a.flags & VCRT_FLAG_STATIC_KERNEL)) {   // VCRT_FLAG_MEGAKERNEL
         // persistent warps: one resident wave, grid = SM count x resident blocks per SM
-        static int grid = 0;
-        if (grid == 0) {
-            int dev = 0, sms = 0, per_sm = 0;
-            cudaError_t e;
-            if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
-                (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_persistent_kernel<SHADER, RNG_MODE, TRIG, COUNT>, VCRT_PBLOCK, 0)) != cudaSuccess)
-                return e;
-            grid = sms * (per_sm > 0 ? per_sm : 1);
-        }
+        int grid = 0;
+        cudaError_t e = persistent_grid((const void*)render_persistent_kernel<SHADER, RNG_MODE, TRIG, COUNT>, VCRT_PBLOCK, &grid, nullptr);
+        if (e != cudaSuccess) return e;
         const uint32_t needed = (items + VCRT_PBLOCK - 1) / VCRT_PBLOCK;
         render_persistent_kernel<SHADER, RNG_MODE, TRIG, COUNT><<<needed < (uint32_t)grid ? needed : (uint32_t)grid, VCRT_PBLOCK, 0, stream>>>(a);
         return cudaGetLastError();
@@ -101,43 +127,52 @@ __global__ void wf_reset_kernel(unsigned int* counts, int which) {
 }
 
 template <int SHADER, int RNG_MODE, int TRIG>
-static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
+static cudaError_t wf_run(const KernelArgs& a, bool count, const WfPipes& pipes, uint32_t* launches, TraceTimer* timer) {
     // the trace variants: [COUNT][QN][PRIMARY]
     typedef void (*TraceFn)(const KernelArgs, const WfQueues, const WfBatch);
     static const TraceFn trace_fn[2][3][2] = {
         {{wf_trace_kernel<false, 0, false>, wf_trace_kernel<false, 0, true>}, {wf_trace_kernel<false, 1, false>, wf_trace_kernel<false, 1, true>}, {wf_trace_kernel<false, 2, false>, wf_trace_kernel<false, 2, true>}},
         {{wf_trace_kernel<true, 0, false>, wf_trace_kernel<true, 0, true>}, {wf_trace_kernel<true, 1, false>, wf_trace_kernel<true, 1, true>}, {wf_trace_kernel<true, 2, false>, wf_trace_kernel<true, 2, true>}}};
-    static int trace_grid[2][3][2] = {{{0, 0}, {0, 0}, {0, 0}}, {{0, 0}, {0, 0}, {0, 0}}}, sms = 0;
-    if (sms == 0) {
-        int dev = 0, per_sm = 0;
-        cudaError_t e;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        for (int c = 0; c < 2; ++c)
-            for (int q = 0; q < 3; ++q)
-                for (int p = 0; p < 2; ++p) {
-                    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_fn[c][q][p], VCRT_PBLOCK, 0)) != cudaSuccess) return e;
-                    trace_grid[c][q][p] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: one resident wave
-                }
-    }
     const int ci = count ? 1 : 0, qi = a.scene.q4nodes ? 2 : a.scene.qnodes ? 1 : 0;
+    int trace_grid[2] = {0, 0}, sms = 0;   // [PRIMARY]; persistent: one resident wave on this device
+    for (int p = 0; p < 2; ++p) {
+        cudaError_t e = persistent_grid((const void*)trace_fn[ci][qi][p], VCRT_PBLOCK, &trace_grid[p], &sms);
+        if (e != cudaSuccess) return e;
+    }
     const uint32_t items = a.owned_tiles * 1024u;
-    const uint32_t per_batch = w.capacity / a.sample_count;   // capacity >= sample_count is guaranteed by the caller
+    const uint32_t per_batch = pipes.q[0].capacity / a.sample_count;   // capacity >= sample_count is guaranteed by the caller
+    const uint32_t nbatches = (items + per_batch - 1) / per_batch;
     const uint32_t shade_grid = (uint32_t)sms * VCRT_SHADE_GRID;
-    for (uint32_t item0 = 0; item0 < items; item0 += per_batch) {
+    // Batches are independent (disjoint pixels): with several pipelines they run side by side on their own streams and queue
+    // sets, so that the tail of one trace launch (its longest rays) overlaps the other pipelines' work.  Pipeline 0 is the
+    // render stream; the others fork from it and join it again (events), so callers see one stream-ordered render.
+    const int use = (int)(nbatches < (uint32_t)pipes.n ? nbatches : (uint32_t)pipes.n);
+    cudaError_t e;
+    if (use > 1) {
+        if ((e = cudaEventRecord(pipes.fork, pipes.stream[0])) != cudaSuccess) return e;
+        for (int s = 1; s < use; ++s)
+            if ((e = cudaStreamWaitEvent(pipes.stream[s], pipes.fork, 0)) != cudaSuccess) return e;
+    }
+    uint32_t bi = 0;
+    for (uint32_t item0 = 0; item0 < items; item0 += per_batch, ++bi) {
+        const int si = use > 1 ? (int)(bi % (uint32_t)use) : 0;
+        const cudaStream_t stream = pipes.stream[si];
+        const WfQueues& w = pipes.q[si];
         WfBatch b;
         b.item0 = item0;
         b.nitems = items - item0 < per_batch ? items - item0 : per_batch;
         b.npaths = b.nitems * a.sample_count;
         b.cur = 0u; b.bounce = 0u;
-        cudaError_t e;
         for (uint32_t bounce = 0; bounce < a.env.max_bounces; ++bounce) {
             b.bounce = bounce;
-            const int pi = bounce == 0u ? 1 : 0;   // bounce 0 reads no queue: rays are generated from the path id
+            const int pi = bounce == 0u ? 1 : 0;   // bounce 0 reads no queue: one primary ray per pixel, generated from the item id
             wf_reset_kernel<<<1, 1, 0, stream>>>(w.counts, (int)(b.cur ^ 1u));
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (timer && (e = timer->begin(stream, &t0, &t1)) != cudaSuccess) return e;
-            trace_fn[ci][qi][pi]<<<trace_grid[ci][qi][pi], VCRT_PBLOCK, 0, stream>>>(a, w, b);
-            if (timer && (e = timer->end(stream, t0, t1)) != cudaSuccess) return e;
+            const uint32_t rays_max = pi ? b.nitems : b.npaths;   // no more blocks than there can be rays (small frames)
+            const uint32_t need = (rays_max + VCRT_PBLOCK - 1) / VCRT_PBLOCK;
+            trace_fn[ci][qi][pi]<<<need < (uint32_t)trace_grid[pi] ? need : (uint32_t)trace_grid[pi], VCRT_PBLOCK, 0, stream>>>(a, w, b);
+            if (timer && (e = timer->end(stream, t0, t1, pi != 0)) != cudaSuccess) return e;
             if (pi) wf_shade_kernel<SHADER, RNG_MODE, TRIG, true><<<shade_grid, 256, 0, stream>>>(a, w, b);
             else wf_shade_kernel<SHADER, RNG_MODE, TRIG, false><<<shade_grid, 256, 0, stream>>>(a, w, b);
             *launches += 3;
@@ -147,29 +182,30 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, cudaStream_t stream, 
         ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    if (use > 1)
+        for (int s = 1; s < use; ++s) {
+            if ((e = cudaEventRecord(pipes.join[s], pipes.stream[s])) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(pipes.stream[0], pipes.join[s], 0)) != cudaSuccess) return e;
+        }
     return cudaSuccess;
 }
 
 template <int SHADER, int RNG_MODE>
-static cudaError_t wf_trig(const KernelArgs& a, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
-    if (trig == VCRT_TRIG_PORTABLE) return wf_run<SHADER, RNG_MODE, VCRT_TRIG_PORTABLE>(a, count, stream, w, launches, timer);
-    return wf_run<SHADER, RNG_MODE, VCRT_TRIG_LIBM>(a, count, stream, w, launches, timer);
+static cudaError_t wf_trig(const KernelArgs& a, int trig, bool count, const WfPipes& pipes, uint32_t* launches, TraceTimer* timer) {
+    if (trig == VCRT_TRIG_PORTABLE) return wf_run<SHADER, RNG_MODE, VCRT_TRIG_PORTABLE>(a, count, pipes, launches, timer);
+    return wf_run<SHADER, RNG_MODE, VCRT_TRIG_LIBM>(a, count, pipes, launches, timer);
 }
 
 template <int SHADER>
-static cudaError_t wf_rng(const KernelArgs& a, int rng, int trig, bool count, cudaStream_t stream, const WfQueues& w, uint32_t* launches, TraceTimer* timer) {
-    if (rng == VCRT_RNG_PHILOX) return wf_trig<SHADER, VCRT_RNG_PHILOX>(a, trig, count, stream, w, launches, timer);
-    return wf_trig<SHADER, VCRT_RNG_PCG_REF>(a, trig, count, stream, w, launches, timer);
+static cudaError_t wf_rng(const KernelArgs& a, int rng, int trig, bool count, const WfPipes& pipes, uint32_t* launches, TraceTimer* timer) {
+    if (rng == VCRT_RNG_PHILOX) return wf_trig<SHADER, VCRT_RNG_PHILOX>(a, trig, count, pipes, launches, timer);
+    return wf_trig<SHADER, VCRT_RNG_PCG_REF>(a, trig, count, pipes, launches, timer);
 }
 
-cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream,
-                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches,
-                                    TraceTimer* timer) {
-    if (a.owned_tiles == 0u) return cudaSuccess;
-    WfQueues w;
-    w.q[0] = q0; w.q[1] = q1; w.hit = hit; w.sample_color = sample_color; w.counts = counts; w.capacity = capacity;
-    if (shader == VCRT_SHADER_SIMPLE) return wf_rng<VCRT_SHADER_SIMPLE>(a, rng, trig, count, stream, w, launches, timer);
-    return wf_rng<VCRT_SHADER_FULL>(a, rng, trig, count, stream, w, launches, timer);
+cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, const WfPipes& pipes, uint32_t* launches, TraceTimer* timer) {
+    if (a.owned_tiles == 0u || pipes.n < 1) return cudaSuccess;
+    if (shader == VCRT_SHADER_SIMPLE) return wf_rng<VCRT_SHADER_SIMPLE>(a, rng, trig, count, pipes, launches, timer);
+    return wf_rng<VCRT_SHADER_FULL>(a, rng, trig, count, pipes, launches, timer);
 }
 #endif
 

@@ -8,14 +8,36 @@
 #include "vcrt_tunables.h"
 
 namespace vcrt {
-struct WfQueues;
+
+// One set of wavefront queues (vcrt_wavefront.cuh); owned by the context.
+struct WfQueues {
+    float4* q[2];                 // 3 float4 per ray, two queues (ping-pong)
+    uint2* hit;                   // per ray of the current queue (bounce 0: per work item): {t bits, winning slot or -1}
+    float4* sample_color;         // per path of the batch: final colour (w unused)
+    unsigned int* counts;         // [0],[1]: queue sizes  [2]: trace fetch counter
+    uint32_t capacity;            // paths per batch
+};
+
+// Pipelines of one wavefront render: independent batches (disjoint pixels) run side by side, each on its own stream with its
+// own queue set.  stream[0] is the render stream; the others fork from it and join it again through the events.
+#define VCRT_MAX_PIPES 4
+struct WfPipes {
+    int n;
+    cudaStream_t stream[VCRT_MAX_PIPES];
+    WfQueues q[VCRT_MAX_PIPES];
+    cudaEvent_t fork, join[VCRT_MAX_PIPES];
+};
 
 // CUDA events around every launch of the dominant kernel (wf_trace_kernel), recorded on the launching stream, so that the
 // roofline's kernel duration is measured live in the timed region.  Events are pooled: no creation cost in steady state.
 struct TraceTimer {
+    struct Rec { cudaEvent_t first, second; bool primary; };
     std::vector<cudaEvent_t> pool;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<Rec> pending;
+    double primary_ms = 0.0;      // part of the harvested time that went into bounce-0 launches
+    bool enabled = true;          // option "trace_timing": off = no events around the trace launches
     cudaError_t begin(cudaStream_t stream, cudaEvent_t* t0, cudaEvent_t* t1) {
+        if (!enabled) return cudaSuccess;
         cudaEvent_t* ev[2] = {t0, t1};
         for (cudaEvent_t* e : ev) {
             if (!pool.empty()) { *e = pool.back(); pool.pop_back(); continue; }
@@ -24,15 +46,16 @@ struct TraceTimer {
         }
         return cudaEventRecord(*t0, stream);
     }
-    cudaError_t end(cudaStream_t stream, cudaEvent_t t0, cudaEvent_t t1) {
-        pending.emplace_back(t0, t1);
+    cudaError_t end(cudaStream_t stream, cudaEvent_t t0, cudaEvent_t t1, bool primary) {
+        if (!enabled) return cudaSuccess;
+        pending.push_back({t0, t1, primary});
         return cudaEventRecord(t1, stream);
     }
     // after a stream synchronise: total milliseconds and count of the pending launches; events go back to the pool
     void drain(double* ms, uint64_t* n) {
         for (auto& p : pending) {
             float f = 0.0f;
-            if (cudaEventElapsedTime(&f, p.first, p.second) == cudaSuccess) { *ms += f; ++*n; }
+            if (cudaEventElapsedTime(&f, p.first, p.second) == cudaSuccess) { *ms += f; ++*n; if (p.primary) primary_ms += f; }
             pool.push_back(p.first); pool.push_back(p.second);
         }
         pending.clear();
@@ -42,7 +65,7 @@ struct TraceTimer {
         size_t done = 0;
         while (done < pending.size() && cudaEventQuery(pending[done].second) == cudaSuccess) {
             float f = 0.0f;
-            if (cudaEventElapsedTime(&f, pending[done].first, pending[done].second) == cudaSuccess) { *ms += f; ++*n; }
+            if (cudaEventElapsedTime(&f, pending[done].first, pending[done].second) == cudaSuccess) { *ms += f; ++*n; if (pending[done].primary) primary_ms += f; }
             pool.push_back(pending[done].first); pool.push_back(pending[done].second);
             ++done;
         }
@@ -55,9 +78,7 @@ struct TraceTimer {
     }
 };
 // Wavefront pipeline of the fast traversal (vcrt_wavefront.cuh); queues are owned by the context.
-cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream,
-                                    float4* q0, float4* q1, uint2* hit, float4* sample_color, unsigned int* counts, uint32_t capacity, uint32_t* launches,
-                                    TraceTimer* timer);
+cudaError_t launch_render_wavefront(const KernelArgs& a, int shader, int rng, int trig, bool count, const WfPipes& pipes, uint32_t* launches, TraceTimer* timer);
 cudaError_t launch_render_reference(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_fast(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_brute(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);

@@ -17,6 +17,7 @@ struct KernelArgs {
     uint32_t owned_tiles;                // number of such tiles
     uint32_t sample_begin, sample_count;
     uint32_t accum_mode, philox_seed, flags;
+    uint32_t num_triangles;              // ubo.numTriangles: the loop bound of the brute-force hit_scene (ray-trace-compute.comp:229)
     uchar4* target;                      // binding 1
     uchar4* accum8;                      // binding 2
     float4* accumf;                      // f32 accumulation (sum of samples, w = sample count)
@@ -39,10 +40,10 @@ VCRT_HD bool item_to_pixel(const KernelArgs& a, uint32_t item, uint32_t& x, uint
     return x < a.covW && y < a.covH;
 }
 
-template <int TRAV, bool COUNT>
+template <int SHADER, int TRAV, bool COUNT>
 VCRT_HD bool closest_hit(const KernelArgs& a, const Ray& r, Hit& rec, TraceStats& st) {
     st.rays++;
-    if (TRAV == VCRT_TRAVERSAL_BRUTE_FORCE) return hit_scene(a.scene, r, rec, st);
+    if (TRAV == VCRT_TRAVERSAL_BRUTE_FORCE) return hit_scene<SHADER>(a.scene, a.num_triangles, r, rec, st);
     if (TRAV == VCRT_TRAVERSAL_FAST) return hit_bvh_fast<COUNT>(a.scene, r, rec, st);
     return hit_bvh_reference(a.scene, r, rec, a.env.stack_depth, st);
 }
@@ -58,7 +59,8 @@ VCRT_HD float3 ray_color(const KernelArgs& a, const Ray& primary, Rng& g, TraceS
     cur.d = normalize(primary.d);
     for (uint32_t i = 0; i < a.env.max_bounces; ++i) {
         rng_begin_bounce<RNG_MODE>(g, i);
-        bool hit = closest_hit<TRAV, COUNT>(a, cur, rec, st);
+        bool hit = closest_hit<SHADER, TRAV, COUNT>(a, cur, rec, st);
+        if (i == 0) st.prim++;
         if (i == 0 && aov) {
             if (hit) { aov->triangle = rec.triangle; aov->material = (int32_t)rec.materialIndex; aov->t = rec.t; aov->backFace = (uint32_t)rec.backFaceInt; }
             else { aov->triangle = -1; aov->material = -1; aov->t = 0.0f; aov->backFace = 0u; }

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
     int32_t pending = VCRT_FAST_EMPTY;
     int32_t stack[VCRT_FAST_STACK];
     bool have_ray = false;          // a ray is in flight (or just finished traversal and awaits shading)
-    TraceStats st = {0u, 0u, 0u};
+    TraceStats st = {0u, 0u, 0u, 0u};
 
     for (;;) {
         // =========================================================== S: lanes whose ray is finished (or that have none)
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
                 }
                 if (qn) trav_begin<1>(t, s, cur); else trav_begin<0>(t, s, cur);
                 st.rays++;
+                if (bounce == 0) st.prim++;
             }
         }
         if (__all_sync(FULL, done)) break;

@@ -75,7 +75,11 @@ bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle
         }
     }
     out.bound_depth = out.depth;
-    if (out.depth + 3 > 48) { err = "bvh: depth " + std::to_string(out.depth) + " exceeds the fast traversal stack (45)"; return false; }
+    return true;
+}
+
+bool check_fast_depth(const FastBvh& fb, std::string& err) {
+    if (fb.depth + 3 > 48) { err = "bvh: depth " + std::to_string(fb.depth) + " exceeds the fast traversal stack (45)"; return false; }
     return true;
 }
 

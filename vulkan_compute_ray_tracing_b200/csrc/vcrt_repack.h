@@ -26,8 +26,12 @@ struct FastBvh {
 
 // Walks the tree in the reference's visiting order (right child first, ray-trace-compute.comp:301-306) so that
 // triangle slots are numbered by the reference's tie rank.  Returns false (err set) for trees the fast traversal
-// does not represent: cycles / shared subtrees, leaves that also have children, depth beyond the traversal stack.
+// does not represent: cycles / shared subtrees, leaves that also have children.  The depth of the tree that will be walked
+// (the bound topology, or the SAH rebuild's) is checked separately by check_fast_depth.
 bool build_fast_bvh(const vcrt_bvh_node* bvh, uint32_t nbvh, const vcrt_triangle* tris, uint32_t ntris, FastBvh& out, std::string& err);
+// False (err set) when fb.depth exceeds what the binary traversal stack holds.  Call it on the tree the kernels will walk:
+// a deep or degenerate bound tree is fine as long as the SAH rebuild (depth <= 24 + log2 n) replaces its topology.
+bool check_fast_depth(const FastBvh& fb, std::string& err);
 
 // Same records, but over a topology built here: binned-SAH top-down build over the leaves collected above (their
 // triangles keep their slots = the reference's tie ranks, so results do not change; only the number of nodes a ray
