@@ -28,6 +28,12 @@ The rewrite is purely syntactic -- no arithmetic expression is changed:
   R12 a `vecN(...)` constructor call whose arguments themselves call random() is brace-initialised
       (`vecN{...}`): GLSL evaluates call arguments left to right (GLSL 4.50 spec, 6.1.1), C++ leaves the
       order of `f(a(), b(), c())` unspecified (GCC goes right to left) but guarantees it for braces
+  R13 `--brute-force`: the active `if (hit_bvh(current_ray, rec))` of ray_color becomes the shader's own commented-out
+      alternative one line above it, `if (hit_scene(current_ray, rec))` (ray-trace-compute.comp:322-323)
+  R14 fragment shader interface: `layout(location=N) in T name;` / `out T name;` -> plain members; `layout(binding=N) uniform
+      sampler2D name;` -> `sampler2D name = bindSampler(N);`; `#extension` lines dropped
+  R15 `--enable-denoiser`: in main() of post-process-shader.frag the active `vec4 fragCol = texture(...)` is replaced by the
+      shader's own commented-out line above it, `vec4 fragCol = t * smartDeNoise(...) + (1-t)*texture(...)` (:64-65)
   R11 optional overrides of `#define NUM_BOUNCES n` / `#define MAX_STACK_DEPTH n`
       (BASELINE configs need depth 4/8 and >16 stack for 1M-triangle trees; the verbatim
       variant keeps the shader's values)
@@ -64,7 +70,15 @@ def brace_random_ctor_args(src):
     return ''.join(out)
 
 
-def rewrite(src, src_dir, is_definitions=False, overrides=None):
+def rewrite(src, src_dir, is_definitions=False, overrides=None, brute_force=False, enable_denoiser=False):
+    if brute_force:      # R13 (before comments are stripped: the alternative lives in one)
+        src, n = re.subn(r'//\s*(if \(hit_scene\(current_ray, rec\)\) \{)\s*\n\s*if \(hit_bvh\(current_ray, rec\)\) \{', r'\1', src)
+        if n != 1:
+            raise SystemExit('brute-force: expected exactly one commented hit_scene alternative, found %d' % n)
+    if enable_denoiser:  # R15
+        src, n = re.subn(r'//\s*(vec4 fragCol = t \* smartDeNoise\([^\n]*\n)\s*vec4 fragCol = texture\(texSampler, fragTexCoord\);', r'\1', src)
+        if n != 1:
+            raise SystemExit('enable-denoiser: expected exactly one commented smartDeNoise line, found %d' % n)
     src = strip_comments(src)
     # R2 includes
     def inline(m):
@@ -74,6 +88,10 @@ def rewrite(src, src_dir, is_definitions=False, overrides=None):
     src = re.sub(r'^[ \t]*#include\s+"([^"]+)"[ \t]*$', inline, src, flags=re.M)
     # R1
     src = re.sub(r'^[ \t]*#version[^\n]*$', '', src, flags=re.M)
+    # R14
+    src = re.sub(r'^[ \t]*#extension[^\n]*$', '', src, flags=re.M)
+    src = re.sub(r'layout\s*\(\s*location\s*=\s*\d+\s*\)\s*(?:in|out)\s+(\w+)\s+(\w+)\s*;', r'\1 \2;', src)
+    src = re.sub(r'layout\s*\(\s*binding\s*=\s*(\d+)\s*\)\s*uniform\s+sampler2D\s+(\w+)\s*;', r'sampler2D \2 = bindSampler(\1);', src)
     src = re.sub(r'layout\s*\(\s*local_size_x[^)]*\)\s*in\s*;', '', src)
     # R6 UBO block
     src = re.sub(r'layout\s*\(\s*binding\s*=\s*(\d+)\s*\)\s*uniform\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;',
@@ -114,6 +132,8 @@ def main():
     ap.add_argument('--out', required=True)
     ap.add_argument('--num-bounces', type=int)
     ap.add_argument('--max-stack-depth', type=int)
+    ap.add_argument('--brute-force', action='store_true')
+    ap.add_argument('--enable-denoiser', action='store_true')
     a = ap.parse_args()
     ov = {}
     if a.num_bounces is not None:
@@ -121,7 +141,7 @@ def main():
     if a.max_stack_depth is not None:
         ov['MAX_STACK_DEPTH'] = a.max_stack_depth
     with open(os.path.join(a.src_dir, a.shader)) as f:
-        out = rewrite(f.read(), a.src_dir, overrides=ov)
+        out = rewrite(f.read(), a.src_dir, overrides=ov, brute_force=a.brute_force, enable_denoiser=a.enable_denoiser)
     with open(a.out, 'w') as f:
         f.write('// GENERATED by oracle/ref/glsl2cpp.py from %s -- do not commit\n' % a.shader)
         f.write(out)

@@ -8,6 +8,10 @@
 //   * sqrt / division IEEE-754 fp32, sin/cos/tan = libm sinf/cosf/tanf, no FMA contraction
 //   * rgba8 imageLoad = c / 255.0f; imageStore = clamp -> *255 -> round-half-even; NaN -> 0
 //   * out-of-range SSBO reads return zero (robustBufferAccess); buffer.length() is host-provided
+//   * texture(sampler2D, uv) = the reference's sampler (Image.cpp:353-364: LINEAR mag/min filter, REPEAT addressing, normalised
+//     coordinates, one mip level) evaluated as the Vulkan specification states it (texel coordinate u*W - 0.5, floor + fraction,
+//     weights at 8 bits of sub-texel precision = VkPhysicalDeviceLimits::subTexelPrecisionBits of every desktop driver and of
+//     lavapipe, the four taps combined in the order of the spec's formula), texels = c / 255.0f
 #pragma once
 #define GLM_FORCE_SWIZZLE
 #include <glm/glm.hpp>
@@ -45,6 +49,26 @@ inline void imageStore(const image2D& im, ivec2 p, vec4 v) {
     c[0] = unorm8(v.x); c[1] = unorm8(v.y); c[2] = unorm8(v.z); c[3] = unorm8(v.w);
 }
 
+struct sampler2D {
+    const uint8_t* data;   // rgba8
+    int w, h;
+};
+inline ivec2 textureSize(const sampler2D& s, int) { return ivec2(s.w, s.h); }
+inline vec4 samplerTexel(const sampler2D& s, int x, int y) {   // VK_SAMPLER_ADDRESS_MODE_REPEAT
+    x %= s.w; if (x < 0) x += s.w;
+    y %= s.h; if (y < 0) y += s.h;
+    const uint8_t* c = s.data + 4 * (size_t(y) * s.w + x);
+    return vec4(c[0] / 255.0f, c[1] / 255.0f, c[2] / 255.0f, c[3] / 255.0f);
+}
+inline vec4 texture(const sampler2D& s, vec2 uv) {   // VK_FILTER_LINEAR
+    const float u = uv.x * float(s.w) - 0.5f, v = uv.y * float(s.h) - 0.5f;
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = rintf((u - fu) * 256.0f) / 256.0f, b = rintf((v - fv) * 256.0f) / 256.0f;
+    const int i0 = (int)fu, j0 = (int)fv;
+    return ((1.0f - a) * (1.0f - b)) * samplerTexel(s, i0, j0) + (a * (1.0f - b)) * samplerTexel(s, i0 + 1, j0) +
+           ((1.0f - a) * b) * samplerTexel(s, i0, j0 + 1) + (a * b) * samplerTexel(s, i0 + 1, j0 + 1);
+}
+
 template <typename T>
 struct Ssbo {
     const T* p;
@@ -66,7 +90,7 @@ inline vec4 operator*(const vec4& v, uint s) { return v * float(s); }
 
 struct Bindings {
     const void* ubo;
-    image2D images[3];              // [1] target, [2] accumulation
+    image2D images[3];              // [1] target, [2] accumulation; the post-process pass samples images[0] (its binding 0)
     const void* ssbo[8];            // [3..7]
     int ssboCount[8];
     int ssboLen[8];
@@ -77,5 +101,6 @@ struct InvocationBase {
     const Bindings* B;
     template <typename U> U bindUbo(int) const { U u; static_assert(sizeof(U) == 32, "std140 UBO"); std::memcpy(&u, B->ubo, sizeof(U)); return u; }
     image2D bindImage(int b) const { return B->images[b]; }
+    sampler2D bindSampler(int b) const { return sampler2D{B->images[b].data, B->images[b].w, B->images[b].h}; }
     template <typename T> Ssbo<T> bindSsbo(int b) const { return Ssbo<T>{(const T*)B->ssbo[b], B->ssboCount[b], B->ssboLen[b]}; }
 };

@@ -507,10 +507,14 @@ void vcrt_oracle_random(uint32_t seed, int n, float* out) {
 
 /* ---------------------------------------------------------------- post-process pass
  * post-process-shader.frag:26-70 restated: smartDeNoise (:26-60; commented out of main at :64) blended with the plain
- * texel by `mix`, then pow(rgb, 1/gamma), alpha 1 (:67-68).  `tex` is the rgba8 target sampled as the reference's sampler
- * does (Image.cpp:353-364): normalised texels, LINEAR filter, REPEAT addressing.  The full-screen quad puts fragment
- * (px, py) at texel centre (px, py); the kernel offsets are integral in x and fractional in y (y starts at -sqrt(r^2-x^2)),
- * so only the y direction interpolates.  Canonical filter arithmetic: fp32, weight = frac(y), a*(1-w) + b*w. */
+ * texel by `mix`, then pow(rgb, 1/gamma), alpha 1 (:67-68).  PINNED: oracle/_ref compiles the fragment shader's own text
+ * (as shipped, and with its commented-out denoiser line enabled) and tests/test_oracle.py requires this restatement to
+ * reproduce its frames bit for bit.
+ * `tex` is the rgba8 target sampled as the reference's sampler does (Image.cpp:353-364): normalised coordinates, LINEAR
+ * filter, REPEAT addressing, evaluated as the Vulkan specification writes it -- texel coordinate u*W - 0.5, floor +
+ * fraction, weights at 8 bits of sub-texel precision, the four taps combined in the order of the spec's formula
+ * (oracle/ref/glsl_prelude.hpp: texture()).  The fragment of pixel (px, py) of the full-screen quad (mesh.cpp:58-93) has
+ * fragTexCoord = ((px + 0.5) / W, (py + 0.5) / H). */
 static inline void texel(const uint8_t* tex, int w, int h, int x, int y, float out[4]) {
     x %= w; if (x < 0) x += w;
     y %= h; if (y < 0) y += h;
@@ -518,13 +522,15 @@ static inline void texel(const uint8_t* tex, int w, int h, int x, int y, float o
     for (int c = 0; c < 4; ++c) out[c] = (float)p[c] / 255.0f;
 }
 
-static inline void sample_linear_y(const uint8_t* tex, int w, int h, int x, float y, float out[4]) {
-    float fy = floorf(y);
-    float wy = y - fy;
-    float a[4], b[4];
-    texel(tex, w, h, x, (int)fy, a);
-    texel(tex, w, h, x, (int)fy + 1, b);
-    for (int c = 0; c < 4; ++c) out[c] = a[c] * (1.0f - wy) + b[c] * wy;
+static inline void texture_linear(const uint8_t* tex, int w, int h, float uvx, float uvy, float out[4]) {
+    const float u = uvx * (float)w - 0.5f, v = uvy * (float)h - 0.5f;
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = rintf((u - fu) * 256.0f) / 256.0f, b = rintf((v - fv) * 256.0f) / 256.0f;
+    const int i0 = (int)fu, j0 = (int)fv;
+    float t00[4], t10[4], t01[4], t11[4];
+    texel(tex, w, h, i0, j0, t00); texel(tex, w, h, i0 + 1, j0, t10); texel(tex, w, h, i0, j0 + 1, t01); texel(tex, w, h, i0 + 1, j0 + 1, t11);
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    for (int c = 0; c < 4; ++c) out[c] = ((w00 * t00[c] + w10 * t10[c]) + w01 * t01[c]) + w11 * t11[c];
 }
 
 int vcrt_oracle_post_process(const uint8_t* tex, uint32_t width, uint32_t height, float mix, float sigma, float kSigma, float threshold,
@@ -535,8 +541,9 @@ int vcrt_oracle_post_process(const uint8_t* tex, uint32_t width, uint32_t height
 #pragma omp parallel for schedule(static)
     for (int py = 0; py < h; ++py)
         for (int px = 0; px < w; ++px) {
+            const float uvx = ((float)px + 0.5f) / (float)w, uvy = ((float)py + 0.5f) / (float)h;
             float centr[4];
-            texel(tex, w, h, px, py, centr);
+            texture_linear(tex, w, h, uvx, uvy, centr);
             float col[4] = {centr[0], centr[1], centr[2], centr[3]};
             if (mix != 0.0f) {
                 float radius = roundf(kSigma * sigma);
@@ -551,9 +558,9 @@ int vcrt_oracle_post_process(const uint8_t* tex, uint32_t width, uint32_t height
                     for (float y = -pt; y <= pt; y += 1.0f) {
                         float blurFactor = expf(-(x * x + y * y) * invSigmaQx2) * invSigmaQx2PI;
                         float walk[4];
-                        sample_linear_y(tex, w, h, px + (int)x, (float)py + y, walk);
+                        texture_linear(tex, w, h, uvx + x / (float)w, uvy + y / (float)h, walk);
                         float dC[4] = {walk[0] - centr[0], walk[1] - centr[1], walk[2] - centr[2], walk[3] - centr[3]};
-                        float dd = ((dC[0] * dC[0] + dC[1] * dC[1]) + dC[2] * dC[2]) + dC[3] * dC[3];
+                        float dd = (dC[0] * dC[0] + dC[1] * dC[1]) + (dC[2] * dC[2] + dC[3] * dC[3]);   /* glm::dot(vec4, vec4) */
                         float deltaFactor = expf(-dd * invThresholdSqx2) * invThresholdSqrt2PI * blurFactor;
                         zBuff += deltaFactor;
                         for (int c = 0; c < 4; ++c) aBuff[c] += deltaFactor * walk[c];

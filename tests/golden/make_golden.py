@@ -14,6 +14,12 @@ Outputs (all small, committed):
                                    the product's scene library (vcrt_scene_load_obj / vcrt_scene_build_bvh), whose output for the
                                    default scene is checked to equal ref_scene_dump's bit for bit
   ref_glass_full_b8_s16_800x600_f2.png   the reference shader's frame for that scene (depth 8, 2 frames)
+  ref_post_800x600_f4.png, ref_post_denoise_800x600_f4.png
+                                   the reference's post-process fragment shader (post-process-shader.frag compiled by oracle/_ref)
+                                   over ref_full_b2_s16_800x600_f4.png: as shipped (gamma 2.2) and with its own commented-out
+                                   smartDeNoise line enabled (:64)
+  ref_brute_96x64.npz              frames of the shader with its commented-out brute-force hit_scene line enabled (:322), full and
+                                   simple, on a 30-triangle scene with one sphere; ubo.numTriangles = all and = 20
   ref_hits.npz                     reference hit_bvh records for 4096 seeded rays (primary + random)
   ref_facts.json                   PCG stream KATs and primary-hit material histograms
 """
@@ -57,6 +63,20 @@ def main():
     save_scene(os.path.join(HERE, "doge_glass_scene.vcrt"), glass)
     img = ref.render_frames("full_b8_s16", glass, CAM, 800, 600, 2)
     Image.fromarray(img, "RGBA").save(os.path.join(HERE, "ref_glass_full_b8_s16_800x600_f2.png"), optimize=True)
+
+    # post-process pass over the 4-frame golden
+    f4 = np.array(Image.open(os.path.join(HERE, "ref_full_b2_s16_800x600_f4.png")).convert("RGBA"))
+    Image.fromarray(ref.post_process(f4, denoise=False), "RGBA").save(os.path.join(HERE, "ref_post_800x600_f4.png"), optimize=True)
+    Image.fromarray(ref.post_process(f4, denoise=True), "RGBA").save(os.path.join(HERE, "ref_post_denoise_800x600_f4.png"), optimize=True)
+
+    # brute-force hit_scene (the shader's commented-out alternative), seeded test scene (tests/tinybvh.py)
+    from tinybvh import build_scene
+    sc = build_scene(30, 4)
+    brute = {}
+    for variant in ("full_b2_s16_brute", "simple_b4_s16_brute"):
+        for nt in (None, 20):
+            brute["%s_%s" % (variant, "all" if nt is None else nt)] = ref.render_frames(variant, sc, (0.0, 6.0, 1.5), 96, 64, 2, num_triangles=nt)
+    np.savez_compressed(os.path.join(HERE, "ref_brute_96x64.npz"), **brute)
 
     rs = np.random.RandomState(1234)
     n = 4096

@@ -20,9 +20,9 @@ class GpuScene:
         self.material = m
         self.model = vcrt.ComputeModel(m)
 
-    def set_camera(self, cam, sample=0):
+    def set_camera(self, cam, sample=0, num_triangles=None):
         """updateScene() of main.cpp:166-183: write the 32-byte UBO into the bundle's buffer."""
-        self.model.getMaterial().getUniformBufferBundles()[0].data.buffers[0].write(vcrt.pack_ubo(cam, sample, self.scene))
+        self.model.getMaterial().getUniformBufferBundles()[0].data.buffers[0].write(vcrt.pack_ubo(cam, sample, self.scene, num_triangles=num_triangles))
 
     def frames(self, cam, n, full_cover=True):
         """The reference frame loop: one computeCommand per frame with currentSample = frame index."""
@@ -36,9 +36,10 @@ class GpuScene:
     def render(self, cam, **kw):
         want_aov = kw.pop("want_aov", False)
         clear = kw.pop("clear", True)
+        num_triangles = kw.pop("num_triangles", None)
         kw["flags"] = kw.get("flags", 0) | (vcrt.FLAG_WRITE_AOV if want_aov else 0)
         p = vcrt.render_params(**kw)
-        self.set_camera(cam, 0)
+        self.set_camera(cam, 0, num_triangles)
         if clear:
             self.material.clearAccum()
         self.material.resetCounters()

@@ -57,12 +57,12 @@ def make_params(shader="full", traversal="reference", rng="pcg_ref", accum="rgba
     return p
 
 
-def make_ubo(cam_pos, scene, current_sample=0):
+def make_ubo(cam_pos, scene, current_sample=0, num_triangles=None):
     u = Ubo()
     u.camPos[0], u.camPos[1], u.camPos[2] = cam_pos
     u.time = 0.0
     u.currentSample = current_sample
-    u.numTriangles = len(scene["triangles"]) // 48
+    u.numTriangles = len(scene["triangles"]) // 48 if num_triangles is None else num_triangles
     u.numLights = len(scene["lights"]) // 8
     u.numSpheres = len(scene["spheres"]) // 32
     return u
@@ -92,10 +92,10 @@ class Oracle:
         s.num_spheres = len(scene["spheres"]) // 32
         return s
 
-    def render(self, scene, cam_pos, w, h, params, target=None, accum8=None, accumf=None, want_aov=False):
-        """Returns dict(target, accum8, accumf, aov, counters)."""
+    def render(self, scene, cam_pos, w, h, params, target=None, accum8=None, accumf=None, want_aov=False, num_triangles=None):
+        """Returns dict(target, accum8, accumf, aov, counters).  num_triangles: ubo.numTriangles when it differs from the buffer length."""
         s = self.scene_struct(scene)
-        u = make_ubo(cam_pos, scene)
+        u = make_ubo(cam_pos, scene, num_triangles=num_triangles)
         if target is None:
             target = np.zeros((h, w, 4), np.uint8)
         if accum8 is None:

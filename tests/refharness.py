@@ -41,10 +41,10 @@ def load_scene(path):
     return out
 
 
-def pack_ubo(cam_pos, current_sample, scene, time=0.0):
+def pack_ubo(cam_pos, current_sample, scene, time=0.0, num_triangles=None):
     """std140 UBO of ray-trace-compute.comp:8-15 / main.cpp:39-47 (32 bytes)."""
     return struct.pack("<3ffIIII", cam_pos[0], cam_pos[1], cam_pos[2], time, current_sample,
-                       len(scene["triangles"]) // 48, len(scene["lights"]) // 8, len(scene["spheres"]) // 32)
+                       len(scene["triangles"]) // 48 if num_triangles is None else num_triangles, len(scene["lights"]) // 8, len(scene["spheres"]) // 32)
 
 
 def have_ref():
@@ -81,16 +81,28 @@ class Ref:
         fn.restype = None
         fn(C.byref(b), gx, gy)
 
-    def render_frames(self, variant, scene, cam_pos, w, h, frames, lights_length=None, full_cover=True):
+    def render_frames(self, variant, scene, cam_pos, w, h, frames, lights_length=None, full_cover=True, num_triangles=None):
         """The reference frame loop (main.cpp:166-183, :228, :253-261): dispatch, then target->accum copy."""
         target = np.zeros((h, w, 4), np.uint8)
         accum = np.zeros((h, w, 4), np.uint8)
         gx = (w + 31) // 32 if full_cover else w // 32
         gy = (h + 31) // 32 if full_cover else h // 32
         for s in range(frames):
-            self.dispatch(variant, scene, pack_ubo(cam_pos, s, scene), target, accum, gx, gy, lights_length)
+            self.dispatch(variant, scene, pack_ubo(cam_pos, s, scene, num_triangles=num_triangles), target, accum, gx, gy, lights_length)
             accum[...] = target
         return target
+
+    def post_process(self, tex, denoise=False):
+        """The reference's post-process fragment shader over the rgba8 image `tex`: as shipped (gamma 2.2 only) or with its own
+        commented-out smartDeNoise line enabled (post-process-shader.frag:64: mix 0.5, sigma 2, kSigma 2, threshold 0.05)."""
+        tex = np.ascontiguousarray(tex, np.uint8)
+        h, w = tex.shape[:2]
+        out = np.zeros_like(tex)
+        fn = getattr(self.lib, "ref_post_denoise" if denoise else "ref_post")
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        fn.restype = None
+        fn(tex.ctypes.data, w, h, out.ctypes.data)
+        return out
 
     def hit_bvh(self, variant, scene, org_dir):
         org_dir = np.ascontiguousarray(org_dir, np.float32)

@@ -218,6 +218,153 @@ def test_brute_force_spheres(oracle):
     assert same_bits(a["target"], b["target"]) and same_bits(a["aov"], b["aov"])
 
 
+def test_brute_force_loop_bounds(oracle):
+    """hit_scene's triangle loop runs to ubo.numTriangles (ray-trace-compute.comp:229) -- less than, equal to or beyond what the
+    buffer holds -- and the simple shader's hit_scene has no sphere loop: against the goldens of the reference's own shader
+    text (commented-out hit_scene line enabled) and against the oracle."""
+    from gpuharness import GpuScene
+    gold = np.load(os.path.join(GOLDEN, "ref_brute_96x64.npz"))
+    sc = small_scene(n_tris=30, seed=4)
+    cam = (0.0, 6.0, 1.5)
+    for shader, variant in (("full", "full_b2_s16_brute"), ("simple", "simple_b4_s16_brute")):
+        g = GpuScene(sc, 96, 64, shader="ray-trace-compute" if shader == "full" else "ray-trace-compute-simple")
+        for nt in (None, 20, 50):
+            kw = dict(shader=shader, traversal="brute_force", sample_count=2, accum="rgba8_ref", num_triangles=nt)
+            b = g.render(cam, trig="libm", **kw)["target"]
+            if nt != 50:
+                assert frac_within_1lsb(b, gold["%s_%s" % (variant, "all" if nt is None else nt)]) >= 0.999, (variant, nt)
+            kw.pop("num_triangles")
+            a = oracle.render(sc, cam, 96, 64, make_params(trig="portable", **kw), num_triangles=nt, want_aov=True)
+            b = g.render(cam, trig="portable", num_triangles=nt, want_aov=True, **kw)
+            assert same_bits(a["target"], b["target"]) and same_bits(a["aov"], b["aov"]), (variant, nt)
+        g.close()
+
+
+def test_lights_length_quirk(gpu_doge, oracle, doge):
+    """lights.length() is what the host's descriptor range makes it (ray-trace-compute.comp:76-77, Buffer.h:85: 1
+    for the unmodified reference on a conformant driver), so light sampling only ever picks lights[0].  Golden frame of the
+    reference shader rendered with that length; bit-exact against the oracle in portable-trig mode on every kernel."""
+    want = load_png("ref_full_b2_s16_800x600_f2_lights1.png")
+    kw = dict(shader="full", sample_count=2, accum="rgba8_ref", rng="pcg_ref", lights_length=1)
+    got = gpu_doge.render(CAM, traversal="fast", trig="libm", **kw)["target"]
+    assert frac_within_1lsb(got, want) >= 0.999 and np.array_equal(got[..., 3], want[..., 3])
+    both = load_png("ref_full_b2_s16_800x600_f4.png")
+    assert not np.array_equal(want, both)
+    a = oracle.render(doge, CAM, 800, 600, make_params(traversal="reference", trig="portable", **kw))["target"]
+    for trav in ("reference", "fast", "fast_mega", "fast_static"):
+        b = gpu_doge.render(CAM, trig="portable", **trav_kw(trav), **kw)["target"]
+        assert np.array_equal(a, b), trav
+    deep = dict(kw, max_bounces=8, sample_count=3, accum="f32", rng="philox")      # the wavefront pipeline
+    a = oracle.render(doge, CAM, 800, 600, make_params(traversal="reference", trig="portable", **deep))["accumf"]
+    b = gpu_doge.render(CAM, traversal="fast", trig="portable", **deep)["accumf"]
+    c = gpu_doge.render(CAM, traversal="fast", trig="portable", **dict(deep, lights_length=0))["accumf"]
+    assert same_bits(a, b) and not same_bits(b, c)
+
+
+def test_duplicate_triangles_tie_rule(oracle):
+    """Every triangle twice: both copies are hit at the same t, and the reference keeps the first leaf of its right-first
+    visiting order (strict `t < closest_so_far`, ray-trace-compute.comp:209).  The fast traversal visits in distance order and
+    resolves the tie by slot rank (vcrt_fast.cuh: trav_leaf_test) -- on the GPU, for every node format and kernel."""
+    from gpuharness import GpuScene
+    import tinybvh
+    sc = small_scene(n_tris=400, seed=9)
+    tri = sc["triangles"].reshape(-1, 48)
+    t2 = np.concatenate([tri, tri]).reshape(-1).copy()
+    sc2 = dict(sc)
+    sc2["triangles"] = t2
+    sc2["bvh"] = tinybvh.build_bvh(t2.view(tinybvh.TRI), seed=5).view(np.uint8).reshape(-1).copy()
+    cam = (0.0, 6.0, 1.5)
+    kw = dict(shader="full", max_bounces=4, sample_count=2, accum="f32", trig="portable", stack_depth=64)
+    a = oracle.render(sc2, cam, 256, 192, make_params(traversal="reference", **kw), want_aov=True)
+    ntri = len(tri)
+    hit = a["aov"]["triangle"][a["aov"]["triangle"] >= 0]
+    assert len(hit) > 10000 and (hit < ntri).any() and (hit >= ntri).any()      # winners come from both copies: not "lowest index wins"
+    g = GpuScene(sc2, 256, 192)
+    for fmt in ("q15x4", "q15", "f32"):
+        g.material.setOption("fast_nodes", fmt)
+        for trav in ("fast", "fast_mega", "fast_static"):
+            b = g.render(cam, want_aov=True, **trav_kw(trav), **kw)
+            assert same_bits(a["aov"], b["aov"]) and same_bits(a["accumf"], b["accumf"]), (fmt, trav)
+    g.material.setOption("fast_nodes", "auto")
+    g.material.setOption("fast_bvh", "topology")
+    b = g.render(cam, want_aov=True, traversal="fast", **kw)
+    g.close()
+    assert same_bits(a["aov"], b["aov"]) and same_bits(a["accumf"], b["accumf"])
+
+
+def test_absent_child_slots(oracle):
+    """Inner nodes with one child, or with a child that has neither triangle nor children, under fast_bvh=topology: the 64-byte
+    float nodes encode the absent slot as the box (+inf, -inf), which must not count as hit (it used to end the traversal early).
+    Every node format, wavefront and one-launch kernels, bit-exact against the oracle."""
+    from gpuharness import GpuScene
+    import tinybvh
+    sc = dict(small_scene(n_tris=900, seed=33))
+    sc["bvh"] = tinybvh.add_degenerate_inner_nodes(sc["bvh"].view(tinybvh.NODE)).view(np.uint8).reshape(-1).copy()
+    cam = (0.0, 6.0, 1.5)
+    kw = dict(shader="full", max_bounces=5, sample_count=2, accum="f32", rng="philox", trig="portable", stack_depth=64)
+    a = oracle.render(sc, cam, 192, 128, make_params(traversal="reference", **kw), want_aov=True)
+    g = GpuScene(sc, 192, 128)
+    for bvh in ("topology", "sah"):
+        g.material.setOption("fast_bvh", bvh)
+        for fmt in ("f32", "q15", "q15x4"):
+            g.material.setOption("fast_nodes", fmt)
+            for trav in ("fast", "fast_mega", "fast_static"):
+                b = g.render(cam, want_aov=True, **trav_kw(trav), **kw)
+                assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (bvh, fmt, trav)
+    g.close()
+
+
+def test_wavefront_pipelines_and_counters(gpu_doge, oracle, doge):
+    """(1) A wavefront render cut into parallel pipelines on 1, 2 or 4 streams (option wf_streams) gives the same bits.
+    (2) Bounce 0 is traced once per pixel and shared by the pixel's samples: `rays` still counts every closest-hit query the
+    shader asks for (equal to the oracle's count), `traversals` what was actually walked."""
+    kw = dict(shader="full", max_bounces=8, sample_count=1, accum="f32", rng="philox", trig="portable")
+    a = oracle.render(doge, CAM, 800, 600, make_params(traversal="reference", **kw))
+    for streams in ("1", "2", "4", "auto"):
+        gpu_doge.material.setOption("wf_streams", streams)
+        b = gpu_doge.render(CAM, traversal="fast", **kw)
+        assert same_bits(a["accumf"], b["accumf"]) and a["counters"].rays == b["counters"].rays, streams
+        assert b["counters"].launches > 1
+    kw["sample_count"] = 4
+    a = oracle.render(doge, CAM, 800, 600, make_params(traversal="reference", **kw))
+    for streams in ("3", "auto"):
+        gpu_doge.material.setOption("wf_streams", streams)
+        b = gpu_doge.render(CAM, traversal="fast", **kw)
+        c = b["counters"]
+        assert same_bits(a["accumf"], b["accumf"]) and a["counters"].rays == c.rays
+        assert c.primary_rays == 800 * 600 * 4 and c.traversals == c.rays - 800 * 600 * 3
+    s = gpu_doge.render(CAM, traversal="fast", flags=8, **kw)["counters"]      # the one-launch kernel walks every query
+    assert s.rays == c.rays and s.traversals == s.rays and s.primary_rays == c.primary_rays
+
+
+def test_c4_size_scene(oracle):
+    """BASELINE.json configs[3] at full size: 10 M triangles (0.8 GB of traversal records: 32-bit slot indices, the q15 extent
+    rule and the stack4 bound of vcrt_repack.cpp in a regime the smaller scenes never reach), 3840x2160, depth 8.  (1) the
+    oracle on 1/256 of the tiles, bit-exact (portable trig); (2) the 4-wide quantised tree and the 64-byte float nodes agree on
+    every bit of the full 4K frame and on the ray count; (3) tile shards partition the frame."""
+    from gpuharness import GpuScene
+    from vulkan_compute_ray_tracing_b200 import scenegen
+    sc = scenegen.generate_box_scene(10000000, seed=1234)
+    w, h = 3840, 2160
+    g = GpuScene(sc, w, h)
+    kw = dict(shader="full", max_bounces=8, sample_count=1, accum="f32", rng="philox", trig="portable", stack_depth=64)
+    full = g.render(CAM, traversal="fast", want_aov=True, **kw)
+    assert g.material.getInfo("fast_nodes") == "q15x4" and int(g.material.getInfo("fast_node_count")) > 2000000
+    a = oracle.render(sc, CAM, w, h, make_params(traversal="reference", tile_rank=77, tile_count=256, **kw), want_aov=True)
+    own = a["accumf"][..., 3] > 0
+    assert own.sum() > 30000 and (a["aov"]["triangle"][own] >= 0).mean() > 0.9
+    assert same_bits(full["accumf"][own], a["accumf"][own]) and same_bits(full["aov"][own], a["aov"][own])
+    b = g.render(CAM, traversal="fast", tile_rank=77, tile_count=256, **kw)
+    assert a["counters"].rays == b["counters"].rays
+    g.material.setOption("fast_nodes", "f32")
+    o = g.render(CAM, traversal="fast", want_aov=True, **kw)
+    assert same_bits(o["accumf"], full["accumf"]) and same_bits(o["aov"], full["aov"]) and o["counters"].rays == full["counters"].rays
+    g.material.setOption("fast_nodes", "auto")
+    parts = [g.render(CAM, traversal="fast", tile_rank=r, tile_count=8, **kw)["accumf"] for r in range(8)]
+    assert same_bits(sum(parts), full["accumf"])
+    g.close()
+
+
 def test_edge_cases(oracle):
     """Empty scene, single triangle, ragged image sizes (not multiples of 32 / 8 / 4)."""
     from gpuharness import GpuScene
@@ -565,6 +712,16 @@ def test_post_process_matches_oracle(gpu_doge, oracle):
     """vcrt_post_process (CUDA) vs the restated fragment shader: gamma-only exactly as shipped, and with smartDeNoise enabled
     as its commented-out call would (mix 0.5, sigma 2, kSigma 2, threshold 0.05).  expf/powf differ by ulps between CUDA and
     glibc: <= 1 LSB on >= 99.9 % of channels, never more than 2."""
+    # the reference's own fragment shader text (oracle/_ref) over the reference's own 4-frame golden, as shipped and with the
+    # denoiser line enabled: the golden is put into the target image through the f32 accumulation (k/255 resolves back to k)
+    gold = load_png("ref_full_b2_s16_800x600_f4.png")
+    gpu_doge.material.clearAccum()
+    gpu_doge.material.writeAccumF32((gold.astype(np.float32) / np.float32(255.0)))
+    gpu_doge.material.resolve(1, 0.0)
+    assert np.array_equal(gpu_doge.target.read(), gold)
+    for name, kw in (("ref_post_800x600_f4.png", dict(mix=0.0, gamma=2.2)), ("ref_post_denoise_800x600_f4.png", dict(mix=0.5, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2))):
+        d = np.abs(gpu_doge.material.postProcess(**kw).astype(int) - load_png(name).astype(int))
+        assert (d <= 1).mean() >= 0.999 and d.max() <= 2, name
     gpu_doge.material.clearAccum()
     img = gpu_doge.frames(CAM, 3)
     for kw in (dict(mix=0.0, gamma=2.2), dict(mix=0.5, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2), dict(mix=1.0, sigma=3.0, k_sigma=2.0, threshold=0.2, gamma=0.0)):

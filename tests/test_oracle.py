@@ -135,6 +135,48 @@ def test_oracle_modes_consistency(oracle, doge):
     assert cover.max() == 1 and cover.min() == 1
 
 
+def test_post_process_reproduces_reference_shader(oracle):
+    """post-process-shader.frag:26-70 -- golden frames written by the reference's own fragment shader text (oracle/_ref), as
+    shipped and with its commented-out smartDeNoise line enabled (:64: mix 0.5, sigma 2, kSigma 2, threshold 0.05): bit-exact."""
+    img = load_png("ref_full_b2_s16_800x600_f4.png")
+    assert np.array_equal(oracle.post_process(img, mix=0.0, gamma=2.2), load_png("ref_post_800x600_f4.png"))
+    den = oracle.post_process(img, mix=0.5, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2)
+    want = load_png("ref_post_denoise_800x600_f4.png")
+    assert np.array_equal(den, want)
+    assert (want != load_png("ref_post_800x600_f4.png")).mean() > 0.01      # the denoiser does something
+
+
+def test_post_process_live_reference_comparison(oracle, ref, doge):
+    """Where oracle/_ref is built: other image sizes (odd sizes: REPEAT addressing at the borders), other frames."""
+    for w, h, n in ((200, 150, 2), (97, 61, 1), (33, 17, 3)):
+        img = oracle.render(doge, CAM, w, h, make_params(shader="full", sample_count=n))["target"]
+        assert np.array_equal(ref.post_process(img, denoise=False), oracle.post_process(img, mix=0.0, gamma=2.2)), (w, h)
+        assert np.array_equal(ref.post_process(img, denoise=True), oracle.post_process(img, mix=0.5, sigma=2.0, k_sigma=2.0, threshold=0.05, gamma=2.2)), (w, h)
+
+
+def test_brute_force_reproduces_reference_shader(oracle):
+    """hit_scene (ray-trace-compute.comp:222-247, the shader's commented-out alternative to hit_bvh at :322): goldens rendered by
+    the reference's own text with that line enabled.  The triangle loop runs to ubo.numTriangles (:229) -- also when that is
+    less than the buffer holds -- the sphere loop restarts from t_max (:238), and the simple shader has no sphere loop."""
+    g = np.load(os.path.join(GOLDEN, "ref_brute_96x64.npz"))
+    sc = small_scene(n_tris=30, seed=4)
+    for shader, variant in (("full", "full_b2_s16_brute"), ("simple", "simple_b4_s16_brute")):
+        for nt in (None, 20):
+            got = oracle.render(sc, (0.0, 6.0, 1.5), 96, 64, make_params(shader=shader, traversal="brute_force", sample_count=2), num_triangles=nt)["target"]
+            assert np.array_equal(got, g["%s_%s" % (variant, "all" if nt is None else nt)]), (variant, nt)
+    assert not np.array_equal(g["full_b2_s16_brute_all"], g["full_b2_s16_brute_20"])
+    assert not np.array_equal(g["full_b2_s16_brute_all"], g["simple_b4_s16_brute_all"])
+
+
+def test_brute_force_live_reference_comparison(oracle, ref):
+    for seed, n, nt in ((5, 12, None), (6, 40, 25), (7, 40, 60)):      # 60 > buffer length: reads past the end return the zero triangle
+        sc = small_scene(n_tris=n, seed=seed)
+        for shader, variant in (("full", "full_b2_s16_brute"), ("simple", "simple_b4_s16_brute")):
+            a = ref.render_frames(variant, sc, (0.0, 6.0, 1.5), 64, 32, 2, num_triangles=nt)
+            b = oracle.render(sc, (0.0, 6.0, 1.5), 64, 32, make_params(shader=shader, traversal="brute_force", sample_count=2), num_triangles=nt)["target"]
+            assert np.array_equal(a, b), (seed, variant, nt)
+
+
 def test_post_process_restatement(oracle, doge):
     """post-process-shader.frag restated: gamma-only path (the shipped shader) against numpy; smartDeNoise keeps flat
     regions, smooths Monte-Carlo noise and leaves hard edges in place."""

@@ -58,9 +58,11 @@ cudaError_t launch_tiles(void* image, void* packed, int elem_bytes, bool pack, u
 // ---------------------------------------------------------------------------------------------- post-process pass
 // post-process-shader.frag:26-70 on the rgba8 target: smartDeNoise (a bilateral filter over a disc of radius
 // round(kSigma*sigma); the shader ships with it commented out of main, :64) blended with the plain texel by `mix`, then
-// pow(rgb, 1/gamma), alpha 1.  Sampling follows the reference's sampler (Image.cpp:353-364: LINEAR, REPEAT): offsets are
-// integral in x and fractional in y, so a tap blends two vertically adjacent texels.  One thread per pixel; the taps of a
-// 16x16 block overlap almost completely, so the rgba8 reads are L1 hits.
+// pow(rgb, 1/gamma), alpha 1.  Sampling follows the reference's sampler (Image.cpp:353-364: normalised coordinates, LINEAR,
+// REPEAT) as the Vulkan specification evaluates it: texel coordinate u*W - 0.5, floor + fraction, weights at 8 bits of
+// sub-texel precision, four taps in the order of the spec's formula -- the same fp32 operations as the oracle, which is
+// pinned to the fragment shader's own text (oracle/_ref).  The fragment of pixel (px, py) has fragTexCoord = pixel centre /
+// image size.  One thread per pixel; the taps of a 16x16 block overlap almost completely, so the rgba8 reads are L1 hits.
 __device__ __forceinline__ float4 post_texel(const uchar4* __restrict__ tex, int w, int h, int x, int y) {
     x %= w; if (x < 0) x += w;
     y %= h; if (y < 0) y += h;
@@ -68,11 +70,24 @@ __device__ __forceinline__ float4 post_texel(const uchar4* __restrict__ tex, int
     return make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, (float)p.w / 255.0f);
 }
 
+__device__ __forceinline__ float4 post_texture(const uchar4* __restrict__ tex, int w, int h, float uvx, float uvy) {
+    const float u = uvx * (float)w - 0.5f, v = uvy * (float)h - 0.5f;
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = rintf((u - fu) * 256.0f) / 256.0f, b = rintf((v - fv) * 256.0f) / 256.0f;
+    const int i0 = (int)fu, j0 = (int)fv;
+    const float4 t00 = post_texel(tex, w, h, i0, j0), t10 = post_texel(tex, w, h, i0 + 1, j0), t01 = post_texel(tex, w, h, i0, j0 + 1),
+                 t11 = post_texel(tex, w, h, i0 + 1, j0 + 1);
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    return make_float4(((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x, ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y,
+                       ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z, ((w00 * t00.w + w10 * t10.w) + w01 * t01.w) + w11 * t11.w);
+}
+
 __global__ void __launch_bounds__(256) post_process_kernel(const uchar4* __restrict__ tex, uchar4* __restrict__ out, int w, int h, float mix, float sigma,
                                                            float kSigma, float threshold, float inv_gamma) {
     const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
     if (px >= w || py >= h) return;
-    const float4 centr = post_texel(tex, w, h, px, py);
+    const float uvx = ((float)px + 0.5f) / (float)w, uvy = ((float)py + 0.5f) / (float)h;
+    const float4 centr = post_texture(tex, w, h, uvx, uvy);
     float col[3] = {centr.x, centr.y, centr.z};
     if (mix != 0.0f) {
         const float radius = roundf(kSigma * sigma), radQ = radius * radius;
@@ -83,11 +98,9 @@ __global__ void __launch_bounds__(256) post_process_kernel(const uchar4* __restr
             const float pt = sqrtf(radQ - x * x);
             for (float y = -pt; y <= pt; y += 1.0f) {
                 const float blurFactor = expf(-(x * x + y * y) * invSigmaQx2) * invSigmaQx2PI;
-                const float sy = (float)py + y, fy = floorf(sy), wy = sy - fy;
-                const float4 a = post_texel(tex, w, h, px + (int)x, (int)fy), b = post_texel(tex, w, h, px + (int)x, (int)fy + 1);
-                const float4 walk = make_float4(a.x * (1.0f - wy) + b.x * wy, a.y * (1.0f - wy) + b.y * wy, a.z * (1.0f - wy) + b.z * wy, a.w * (1.0f - wy) + b.w * wy);
+                const float4 walk = post_texture(tex, w, h, uvx + x / (float)w, uvy + y / (float)h);
                 const float dx = walk.x - centr.x, dy = walk.y - centr.y, dz = walk.z - centr.z, dw = walk.w - centr.w;
-                const float deltaFactor = expf(-(((dx * dx + dy * dy) + dz * dz) + dw * dw) * invThresholdSqx2) * invThresholdSqrt2PI * blurFactor;
+                const float deltaFactor = expf(-((dx * dx + dy * dy) + (dz * dz + dw * dw)) * invThresholdSqx2) * invThresholdSqrt2PI * blurFactor;
                 zBuff += deltaFactor;
                 ax += deltaFactor * walk.x; ay += deltaFactor * walk.y; az += deltaFactor * walk.z;
             }

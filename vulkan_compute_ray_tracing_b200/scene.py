@@ -36,7 +36,7 @@ def save_scene(path, scene):
             f.write(np.ascontiguousarray(scene[n]).view(np.uint8).tobytes())
 
 
-def pack_ubo(cam_pos, current_sample, scene, time=0.0):
-    """UniformBufferObject of main.cpp:39-47 / :174."""
+def pack_ubo(cam_pos, current_sample, scene, time=0.0, num_triangles=None):
+    """UniformBufferObject of main.cpp:39-47 / :174.  numTriangles = rtScene.triangles.size() there; pass num_triangles to differ."""
     return struct.pack("<3ffIIII", cam_pos[0], cam_pos[1], cam_pos[2], time, current_sample,
-                       len(scene["triangles"]) // 48, len(scene["lights"]) // 8, len(scene["spheres"]) // 32)
+                       len(scene["triangles"]) // 48 if num_triangles is None else num_triangles, len(scene["lights"]) // 8, len(scene["spheres"]) // 32)
