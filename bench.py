@@ -5,27 +5,37 @@ Workload at N=1 (BASELINE.json configs[2], "C3"): seeded synthetic 1M-triangle l
 spheres, reference-layout BVH built by the reference's median-split algorithm), 1920x1080, 64 spp, depth 8, full
 shader (Lambertian + light sampling), Philox RNG, f32 accumulation, fast traversal.  One "step" = one 64-spp render
 of the whole frame.  At N>1 the scene is replicated, rank r renders sample slice [r*64, (r+1)*64) of an N*64-spp
-image (weak scaling) and the f32 accumulation buffers are summed onto rank 0 with an NCCL reduce inside the timed
-region.
+image (weak scaling) and the f32 accumulation buffers are summed onto rank 0 with ONE NCCL reduce issued by the library
+(vcrt_group_render) on the render stream, inside the timed region.
 
   value     whole-job Mrays/s with the scene resident in HBM; timed per step with CUDA events on the launch stream
-            (L2 flushed between steps), max over ranks.
+            (L2 flushed between steps), max over ranks.  A "ray" is a closest-hit query of the shader's ray_color
+            (ray-trace-compute.comp:321-323), one per sample and bounce -- the same count the reference arm reports.  The
+            shader's primary ray does not depend on the sample (:352-373, no jitter), so the wavefront pipeline walks the tree
+            once per pixel for bounce 0 and shares the answer among the pixel's samples: `primary_mrays` / `bounce_mrays`
+            give the two populations separately, `traversals_per_step` what was actually walked.
   e2e       the same metric through the public API with HOST buffers, following the reference's frame loop: per step the
             32-byte UBO goes host -> device, the frame is rendered and resolved, and the rgba8 target is read back into
             pinned host memory (scene resident, as after the reference's initScene); `with_scene_upload` also re-uploads the
             five scene buffers and rebuilds the traversal records every step.  Wall clock between synchronised barriers,
             max over ranks.
-  roofline  HBM-bound traversal roofline for the dominant kernel (wf_trace_kernel, timed per launch with CUDA events on
-            its stream inside the timed region): algorithmic bytes per ray B_ray = 48*(nodes + triangles) of the canonical
-            (reference-order, t-culled) traversal, counted by the CPU oracle on a tile sample of the same ray set
-            (SURVEY.md 8d).  The kernel walks a SAH tree rebuilt over the same leaves and fetches far fewer bytes, so
-            `frac` exceeds 1; `own_*` gives the bytes the kernel actually requests (its own node/triangle counters) and
-            `l1_gather` the kernel's 32-byte gather rate against the L1TEX gather ceiling measured by tools/ubench.
+  roofline  for the dominant kernel (wf_trace_kernel, timed per launch with CUDA events on its stream inside the timed
+            region).  C3's working set (21 MB of nodes + 64 MB of triangle records) is L2-resident on a B200, so HBM does not
+            bind it; what does is the rate at which L1TEX pulls divergent 32-byte sectors out of L2.  `peak` is that rate
+            MEASURED IN THIS PROCESS before the timed region (tools/ubench/probe.cu: dependent random 32-byte LDG.256 gathers
+            over a 32 MB L2-resident table, the kernel's own launch shape), `achieved` the kernel's own scene-record sector
+            requests (its node/triangle counters x 2 sectors) per second of kernel time, both x 32 B -> GB/s.
+            `roofline.canonical` keeps SURVEY 8d's figure for the record (48 B x the canonical reference-order traversal's
+            fetches over the measured HBM peak; the kernel walks a 4-wide SAH tree and fetches ~14x fewer bytes, so that
+            fraction is not a ceiling).  `roofline.hbm` = real DRAM bytes per launch (ncu capture committed under profiles/)
+            over kernel time and the measured HBM peak.  `c4` (N=1 only) runs BASELINE configs[3]'s 10M-triangle scene, whose
+            0.8 GB of records do not fit L2, with the same accounting against a DRAM-resident gather probe.
   cpu_baseline / --impl reference
             the reference's own shader text compiled for the CPU (oracle/_ref, kind "reference"; falls back to the
             restated oracle, kind "port") on all host cores, on a bounded sample of the same workload.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -40,15 +50,14 @@ sys.path.insert(0, ROOT)
 
 CAM = (1.8, 8.6, 1.1)   # main.cpp:37
 HBM_FALLBACK_GBS = 6650.0
-L1_GATHER_PEAK_G = 270.0   # measured: profiles/r01_v10_gather_tex_ubench.log (modes L / LL, 32 MB and 2 MB record sets)
 
 
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
     except Exception:
-        return HBM_FALLBACK_GBS, "fallback"
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -94,20 +103,31 @@ def pinned_copy(arr):
     return out, t
 
 
-def build_workload(args):
+def build_workload(args, config=None, triangles=None):
     t0 = time.time()
-    if args.config == "c2":   # BASELINE.json configs[1]: the bundled scene (glass/metal variant, as assembled by csrc/scene from the reference's OBJ files)
+    config = config or args.config
+    if config == "c2":   # BASELINE.json configs[1]: the bundled scene (glass/metal variant, as assembled by csrc/scene from the reference's OBJ files)
         import vulkan_compute_ray_tracing_b200 as vcrt
         scene = vcrt.load_scene(os.path.join(ROOT, "tests", "golden", "doge_glass_scene.vcrt"))
     else:
         from vulkan_compute_ray_tracing_b200 import scenegen
-        scene = scenegen.generate_box_scene(args.triangles, seed=args.scene_seed)
+        scene = scenegen.generate_box_scene(triangles or args.triangles, seed=args.scene_seed)
     return scene, time.time() - t0
 
 
+def set_host_threads(n):
+    """OpenMP threads of everything host-side in this process (launchers such as torchrun export OMP_NUM_THREADS=1, which would
+    serialise the scene generator, the record build and -- 16x slower -- the CPU reference arm)."""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def oracle_bray(scene, w, h, bounces, tile_count):
-    """Algorithmic bytes per ray: canonical (reference order + t-culling) traversal counted by the oracle on 1/tile_count
-    of the 32x32 tiles at 1 spp (pcg_ref), SURVEY.md 8d."""
+    """Algorithmic bytes per ray of SURVEY.md 8d: canonical (reference order + t-culling) traversal counted by the oracle on
+    1/tile_count of the 32x32 tiles at 1 spp (pcg_ref)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracleharness import Oracle, make_params
     o = Oracle()
@@ -152,23 +172,36 @@ def cpu_reference_step(scene, w, h, bounces, frames, first_sample=0):
 
 
 def run_reference_arm(args, rank):
+    """The reference's own CPU implementation of the path (oracle/_ref), all host threads, rank 0 only.  Bounded: every step is
+    `--ref-frames` 1-spp frames of the workload's image (a 1/spp sample of the step), and the whole run is cut short once
+    `--ref-budget` seconds of CPU rendering have been spent, so that it ends within a few minutes on any core count."""
     if rank != 0:
         return
+    set_host_threads(os.cpu_count() or 1)
     subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     scene, _ = build_workload(args)
     frames = args.ref_frames
-    for _ in range(args.warmup):
-        cpu_reference_step(scene, args.width, args.height, args.bounces, 1)
-    tot_t, tot_r, kind = 0.0, 0, "port"
+    spent = 0.0
+    for _ in range(min(args.warmup, 1)):          # one warm-up frame pages the scene in; more would only burn the budget
+        dt, _, _ = cpu_reference_step(scene, args.width, args.height, args.bounces, 1)
+        spent += dt
+    tot_t, tot_r, kind, done = 0.0, 0, "port", 0
     for k in range(args.steps):
         dt, rays, kind = cpu_reference_step(scene, args.width, args.height, args.bounces, frames, first_sample=k * frames)
-        tot_t += dt; tot_r += rays
+        tot_t += dt; tot_r += rays; done += 1
+        if spent + tot_t > args.ref_budget:
+            break
     v = tot_r / tot_t / 1e6
     cores = os.cpu_count()
-    sample = "%d x 1-spp frames of the %dx%d image per step (of %d spp), reference traversal, pcg_ref RNG" % (frames, args.width, args.height, args.spp)
-    line = {"impl": "reference", "metric": "Mrays/s (primary+bounce)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene),
+    sample = "%d step(s) x %d 1-spp frame(s) of the %dx%d image (the workload's step is %d spp), %.1f s of CPU time" % (done, frames, args.width, args.height, args.spp, tot_t)
+    cfg = workload_config(args, scene)
+    cfg["implementation"] = ("the reference's shader text compiled for the host (oracle/_ref, OpenMP over rows, %d threads): PCG RNG of random.glsl, literal hit_bvh "
+                             "on the bound median-split tree with a 32-entry stack, rgba8 running mean; %s" % (cores, sample)) if kind == "reference" else \
+        ("restated oracle (oracle/vcrt_oracle.c), %d threads; %s" % (cores, sample))
+    cfg["sharding"] = "none (rank 0 only)"
+    line = {"impl": "reference", "metric": "Mrays/s (primary+bounce)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": done,
+            "warmup": min(args.warmup, 1), "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": 1e3 * tot_t / max(done, 1), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -199,17 +232,51 @@ def scene_hash(scene):
 
 
 def workload_config(args, scene):
+    """What is rendered (identical for both arms); HOW it is rendered goes into config["implementation"] per arm."""
     spp_txt = "%d spp/GPU" % args.spp if args.scaling == "weak" else "%d spp in total" % args.spp
     shard = {"samples": "sample slices + NCCL reduce of the f32 accumulation buffers", "tiles": "32x32 tile interleave + NCCL all-gather of packed rgba8 tiles"}[args.sharding]
     what = "bundled scene, glass/metal variant (%d triangles)" % (len(scene["triangles"]) // 48) if args.config == "c2" else \
         "synthetic %d-triangle lit box (seed %d)" % (len(scene["triangles"]) // 48, args.scene_seed)
-    return {"workload": "%s: %s, %dx%d, %s, depth %d, full shader, philox, f32 accum, fast traversal"
-                        % (args.config.upper(), what, args.width, args.height, spp_txt, args.bounces),
+    return {"workload": "%s: %s, %dx%d, %s, depth %d, full shader (Lambertian + light sampling)" % (args.config.upper(), what, args.width, args.height, spp_txt, args.bounces),
             "triangles": len(scene["triangles"]) // 48, "bvh_nodes": len(scene["bvh"]) // 48, "width": args.width, "height": args.height,
             "spp": args.spp, "spp_is": "per GPU" if args.scaling == "weak" else "total", "max_bounces": args.bounces,
             "scene_sha256": scene_hash(scene),
-            "sharding": (shard + " (%s)" % args.scaling) if args.gpus > 1 else "none",
+            "sharding": (shard + " (%s), vcrt_group_render" % args.scaling) if args.gpus > 1 else "none",
             "l2": "flushed between timed steps (256 MiB memset)"}
+
+
+class Probe:
+    """tools/ubench/libvcrt_probe.so: peaks measured in this process, on this GPU, before the timed region."""
+
+    def __init__(self, device):
+        path = os.path.join(ROOT, "tools", "ubench", "libvcrt_probe.so")
+        if not os.path.exists(path):
+            subprocess.call(["make", "-C", os.path.dirname(path)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        self.lib = ctypes.CDLL(path)
+        self.device = device
+
+    def gather(self, records_log2, steps=64, chains=1, reps=3):
+        out = ctypes.c_double()
+        rc = self.lib.vcrt_probe_gather(self.device, records_log2, steps, chains, reps, ctypes.byref(out))
+        return out.value if rc == 0 else None
+
+    def stream(self, nbytes, passes=8, reps=3):
+        out = ctypes.c_double()
+        self.lib.vcrt_probe_stream.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        rc = self.lib.vcrt_probe_stream(self.device, nbytes, passes, reps, ctypes.byref(out))
+        return out.value if rc == 0 else None
+
+
+def ncu_traffic(key):
+    """DRAM bytes per trace launch from the committed ncu capture of this round (profiles/ncu_traffic.json; `ncu --metrics
+    dram__bytes_read.sum,dram__bytes_write.sum` over the bench command).  None when no capture is on record for `key`."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        e = d.get(key) or (d if key == "c3" and "dram_bytes_per_launch" in d else None)
+        return e
+    except Exception:
+        return None
 
 
 def main():
@@ -228,9 +295,13 @@ def main():
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--traversal", default="fast")
     ap.add_argument("--ref-frames", type=int, default=1, help="1-spp frames per step of the CPU reference arm")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of CPU rendering after which the reference arm stops early")
     ap.add_argument("--static-kernel", action="store_true", help="A/B: one-thread-per-pixel launch of the fast traversal")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the HBM-sized C4 leg of the N=1 run")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record of an N>1 run")
+    ap.add_argument("--option", action="append", default=[], help="key=value for vcrt_set_option (A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     for k, v in CONFIGS[args.config].items():
@@ -240,69 +311,77 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # host-side scene generation / record builds use OpenMP; torchrun exports OMP_NUM_THREADS=1, which would serialise them
-    host_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
-    if args.impl == "ours":
-        os.environ["OMP_NUM_THREADS"] = str(host_threads)
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
+    # host-side scene generation / record builds use OpenMP; torchrun exports OMP_NUM_THREADS=1, which would serialise them
+    host_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+    set_host_threads(host_threads)
 
     import torch
     import torch.distributed as dist
     import vulkan_compute_ray_tracing_b200 as vcrt
+    from vulkan_compute_ray_tracing_b200 import sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # ---- peaks of the levels that can bind the trace kernel, measured here and now (before anything else touches the GPU)
+    probes = None
+    if rank == 0:
+        pr = Probe(local_rank)
+        probes = {"l2_gather_gps": pr.gather(20), "l2_gather_2chains_gps": pr.gather(20, chains=2), "l1_gather_gps": pr.gather(11),
+                  "l2_stream_gbs": pr.stream(48 << 20, passes=16), "hbm_stream_gbs": pr.stream(4 << 30, passes=1),
+                  "how": "tools/ubench/probe.cu in this process: dependent random 32-byte LDG.256 gathers, 148 x 10 x 6 blocks of 128 (table 32 MB: L2-resident, "
+                         "L1-missing; 64 KB: L1-resident); coalesced 128-bit reads of 48 MB (L2) / 4 GB (HBM); best of 3 after a warm-up"}
+
     scene, gen_s = build_workload(args)
     w, h = args.width, args.height
 
-    # ---- host object, as main.cpp:76-153 builds it
-    pinned = {k: pinned_copy(v) for k, v in scene.items()}
-    ubo = vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), vcrt.pack_ubo(CAM, 0, scene))
-    target, accum = vcrt.Image(w, h), vcrt.Image(w, h)
-    mat = vcrt.ComputeMaterial("resources/shaders/generated/ray-trace-compute.spv", device=local_rank)
-    mat.addUniformBufferBundle(ubo)
-    mat.addStorageImage(target)
-    mat.addStorageImage(accum)
+    def make_host_object(sc, ww, hh):
+        """main.cpp:76-153"""
+        ubo_ = vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), vcrt.pack_ubo(CAM, 0, sc))
+        target_, accum_ = vcrt.Image(ww, hh), vcrt.Image(ww, hh)
+        mat_ = vcrt.ComputeMaterial("resources/shaders/generated/ray-trace-compute.spv", device=local_rank)
+        mat_.addUniformBufferBundle(ubo_)
+        mat_.addStorageImage(target_)
+        mat_.addStorageImage(accum_)
+        for name in order:
+            mat_.addStorageBufferBundle(vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), sc[name]))
+        model_ = vcrt.ComputeModel(mat_)
+        mat_.setOption("host_threads", str(host_threads))
+        for kv in args.option:
+            k_, v_ = kv.split("=", 1)
+            mat_.setOption(k_, v_)
+        return ubo_, target_, mat_, model_
+
     order = ("triangles", "materials", "bvh", "lights", "spheres")
-    for name in order:
-        mat.addStorageBufferBundle(vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), scene[name]))
-    model = vcrt.ComputeModel(mat)
-    mat.setOption("host_threads", str(host_threads))
-    stream = torch.cuda.Stream()          # a real (non-default) stream shared by the kernels, NCCL and the timing events
+    pinned = {k: pinned_copy(v) for k, v in scene.items()}
+    ubo, target, mat, model = make_host_object(scene, w, h)
+    stream = torch.cuda.Stream()          # a real (non-default) stream shared by the kernels, the library's NCCL calls and the timing events
     torch.cuda.set_stream(stream)
     mat.setStream(stream.cuda_stream)
+    group = sharding.Group.from_torch(mat) if world > 1 else None
 
-    from vulkan_compute_ray_tracing_b200 import sharding
     # weak scaling: the job is an (spp x world)-sample frame; strong scaling: an spp-sample frame whatever the world size
     total_spp = args.spp * world if args.scaling == "weak" else args.spp
-    base = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
-                              stack_depth=64, sample_begin=0, sample_count=total_spp, philox_seed=args.scene_seed,
-                              flags=vcrt.FLAG_STATIC_KERNEL if args.static_kernel else 0)
-    params, active = sharding.shard_params(base, args.sharding, rank, world)
-    ptr, nbytes = mat.devicePtr(2)
 
-    class _Wrap:
-        __cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "<f4", "data": (ptr, False), "version": 2}
-    accum_t = torch.as_tensor(_Wrap(), device="cuda")
+    def params_for(spp):
+        return vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
+                                  stack_depth=64, sample_begin=0, sample_count=spp, philox_seed=args.scene_seed,
+                                  flags=vcrt.FLAG_STATIC_KERNEL if args.static_kernel else 0)
+    base = params_for(total_spp)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def step():
-        mat.clearAccum()
-        if active:
-            model.renderCommand(None, 0, params)
-        if args.sharding == "samples":
-            if world > 1:
-                sharding.reduce_accumulation(accum_t, dst=0)      # NCCL SUM reduce on the render stream
-            if rank == 0:
-                mat.resolve(total_spp, 0.0)
+    def step(p=base):
+        if group is None:
+            mat.clearAccum()
+            model.renderCommand(None, 0, p)
+            mat.resolve(p.sample_count, 0.0)
         else:
-            mat.resolve(total_spp, 0.0)                           # every rank resolves its own tiles ...
-            sharding.gather_tiles_device(mat, 0, rank, world)     # ... and the packed rgba8 tiles are all-gathered
+            group.render(model, p, args.sharding, 0.0)     # clear + this rank's share + ONE NCCL collective + resolve, all on `stream`
 
     def barrier():
         torch.cuda.synchronize()
@@ -310,44 +389,100 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(p, steps, warmup):
+        for _ in range(warmup):
+            step(p)
+        barrier()
+        mat.resetCounters()
+        evs = []
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step(p)
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        wall_ = time.perf_counter() - t0
+        dev_ms_ = sum(a.elapsed_time(b) for a, b in evs)
+        c_ = mat.counters()
+        tot_ = torch.tensor([float(c_.rays), float(c_.launches), float(c_.traversals), float(c_.primary_rays)], dtype=torch.float64, device="cuda")
+        mx_ = torch.tensor([dev_ms_, wall_ * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot_, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx_, op=dist.ReduceOp.MAX)
+        return c_, [float(x) for x in tot_], float(mx_[0])
+
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step()
     barrier()
-    mat.resetCounters()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    evs = []
-    barrier()
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step()
-        e1.record(stream)
-        evs.append((e0, e1))
-    barrier()
-    wall = time.perf_counter() - wall0
+    c, tot, max_ms = timed_steps(base, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    c = mat.counters()
     rays, kernel_ms, launches = int(c.rays), float(c.kernel_ms), int(c.launches)
     trace_ms, trace_launches = float(c.trace_ms), int(c.trace_launches)
-    tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device="cuda")
-    mx = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    total_rays, total_launches = float(tot[0]), int(tot[1])
-    max_ms = float(mx[0])
+    total_rays, total_launches, total_trav, total_prim = tot[0], int(tot[1]), tot[2], tot[3]
     value = total_rays / (max_ms * 1e-3) / 1e6
+
+    # ---- correctness of the combined multi-GPU frame (outside the timed region): the N-GPU frame against ONE GPU rendering the
+    # same samples.  Tile shards: bit-identical on every rank; sample slices: same sample set, fp32 summation order differs ->
+    # the resolved rgba8 frames agree within 1 LSB.
+    frame_check = None
+    if world > 1:
+        step()
+        mat.synchronize()
+        got = target.read() if (rank == 0 or args.sharding == "tiles") else None
+        ok = True
+        detail = None
+        if got is not None:
+            mat.clearAccum()
+            model.renderCommand(None, 0, base)
+            mat.resolve(total_spp, 0.0)
+            want = target.read()
+            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            ok = bool(d.max() == 0) if args.sharding == "tiles" else bool(d.max() <= 1)
+            detail = {"max_abs_diff_lsb": int(d.max()), "differing_channels": int((d > 0).sum()), "sha256_combined": __import__("hashlib").sha256(got.tobytes()).hexdigest()[:16]}
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        frame_check = {"frame_matches_1gpu": bool(flag.item() == 1.0), "rule": "bit-identical on every rank" if args.sharding == "tiles" else "rgba8 within 1 LSB on rank 0",
+                       "samples_compared": total_spp, **(detail or {})}
+
+    # ---- strong scaling (N > 1): the SAME spp-sample frame split over the N GPUs, collective included, and -- the anchor --
+    # that frame on rank 0's GPU alone, in the same run
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        ps = params_for(args.spp)
+        _, tot_s, ms_s = timed_steps(ps, args.steps, 2)
+        one_ms = 0.0
+        if rank == 0:
+            def one():
+                mat.clearAccum(); model.renderCommand(None, 0, ps); mat.resolve(args.spp, 0.0)
+            for _ in range(2):
+                one()
+            mat.synchronize()
+            evs = []
+            for _ in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); one(); e1.record(stream)
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            one_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        barrier()
+        strong = {"what": "the %d-spp frame of the N=1 workload split over %d GPUs (%s), collective and resolve inside the timed region" % (args.spp, world, args.sharding),
+                  "ms_per_step": ms_s / args.steps, "value": tot_s[0] / (ms_s * 1e-3) / 1e6, "unit": "Mrays/s", "spp_total": args.spp, "steps": args.steps,
+                  "n1_ms_per_step_same_run": one_ms, "speedup_vs_n1_same_run": one_ms / (ms_s / args.steps) if ms_s > 0 else None,
+                  "efficiency_vs_n1_same_run": one_ms / (ms_s / args.steps) / world if ms_s > 0 else None}
 
     # ---- e2e: through the public API with host buffers, host<->device copies inside the timed region.
     # Headline protocol = the reference's own frame loop (main.cpp:166-183, :228, :323-395), which is also what the reference
     # arm times: scene prepared once outside the timed region; per step the 32-byte UBO goes host -> device, the frame is
     # rendered and resolved, and the rgba8 target comes back into pinned host memory.  `with_scene_upload` additionally
-    # re-uploads the five scene buffers from pinned host memory and rebuilds the traversal records on the host every step.
+    # re-uploads the five scene buffers from pinned host memory and rebuilds the traversal records every step.
     e2e = None
     if not args.no_e2e:
         out_host = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
@@ -388,8 +523,7 @@ def main():
                "protocol": "reference frame loop: UBO write + computeCommand-equivalent render + resolve + rgba8 read-back to pinned host memory; scene resident"}
         # the reference's own unit of work, "ms/frame" (main.cpp:397-413): one 1-spp frame per iteration of the frame loop --
         # UBO with the frame's sample index in, one sample rendered on top of the accumulation, resolve, rgba8 frame back
-        one = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
-                                 stack_depth=64, sample_begin=0, sample_count=1, philox_seed=args.scene_seed)
+        one = params_for(1)
         if world == 1:
             def one_frame(k):
                 ubo.buffers[0].write(vcrt.pack_ubo(CAM, k, scene))
@@ -397,71 +531,153 @@ def main():
                 model.renderCommand(None, 0, one)
                 mat.resolve(k + 1, 0.0)
                 mat._check(L.vcrt_read_target_rgba8(mat._ctx, out_host.ctypes.data, out_host.nbytes))
-            mat.clearAccum()
-            for k in range(4):
-                one_frame(k)
-            mat.resetCounters()
-            nfr = 32
-            t0 = time.perf_counter()
-            for k in range(4, 4 + nfr):
-                one_frame(k)
-            dt = time.perf_counter() - t0
-            e2e["frame_1spp"] = {"ms_per_frame": 1e3 * dt / nfr, "value": mat.counters().rays / dt / 1e6, "unit": "Mrays/s", "frames": nfr,
+
+            def frame_loop(nfr):
+                mat.clearAccum()
+                for k in range(4):
+                    one_frame(k)
+                mat.resetCounters()
+                t0 = time.perf_counter()
+                for k in range(4, 4 + nfr):
+                    one_frame(k)
+                dt = time.perf_counter() - t0
+                return 1e3 * dt / nfr, mat.counters().rays / dt / 1e6
+            nfr = 64
+            ms1, v1 = frame_loop(nfr)
+            e2e["frame_1spp"] = {"ms_per_frame": ms1, "value": v1, "unit": "Mrays/s", "frames": nfr, "wf_streams": "auto (4 parallel pipelines)",
                                  "protocol": "progressive frame loop, one sample per frame, rgba8 frame read back every frame"}
+            mat.setOption("wf_streams", "1")
+            ms1s, _ = frame_loop(nfr)
+            mat.setOption("wf_streams", "auto")
+            e2e["frame_1spp"]["ms_per_frame_one_pipeline"] = ms1s
         v, ms = timed(True, min(args.steps, 3))
         e2e["with_scene_upload"] = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
-                                    "includes": "upload of the 5 scene buffers from pinned host memory + host rebuild of the traversal records, every step"}
+                                    "includes": "upload of the 5 scene buffers from pinned host memory + rebuild of the traversal records, every step"}
 
+    def kernel_accounting(mat_, model_, spp_, c_, steps_, step_ms, probes_, cfg_key, hbm_peak):
+        """Roofline records of the dominant kernel from live counters: c_ = counters of the timed region (steps of spp_ samples)."""
+        rays_ = int(c_.rays)
+        trav_ = int(c_.traversals)
+        t_ms, t_n, p_ms = float(c_.trace_ms), int(c_.trace_launches), float(c_.primary_trace_ms)
+        if not t_n:
+            return None
+        # what the kernel itself requests: its node/triangle counters over one more step of the same shape (untimed, counting
+        # build of the kernel; same mix of primary and bounce traversals as the timed steps)
+        cp = params_for(spp_)
+        cp.flags |= vcrt.FLAG_COUNT_TRAVERSAL
+        mat_.clearAccum(); mat_.resetCounters()
+        model_.renderCommand(None, 0, cp)
+        cc = mat_.counters()
+        node_bytes = 32 if mat_.getInfo("fast_nodes") == "q15" else 64
+        tri_bytes = 64
+        sectors_per_trav = ((node_bytes // 32) * cc.nodes + 2.0 * cc.triangles) / max(cc.traversals, 1)
+        kernel_s = t_ms * 1e-3 / t_n
+        trav_per_launch = trav_ / t_n
+        g_rate = sectors_per_trav * trav_ / (t_ms * 1e-3) / 1e9          # G sectors/s over all trace launches of the timed region
+        peak_g = probes_["l2_gather_gps"]
+        rec = {"bound": "l2", "achieved": g_rate * 32.0, "peak": peak_g * 32.0, "unit": "GB/s", "frac": g_rate / peak_g,
+               "what": "scene-record sector requests of the kernel (2 x 32 B per node visit and per triangle test, own counters) x 32 B per second of kernel time, against the "
+                       "rate of dependent random 32-byte gathers from an L2-resident table measured by the in-process probe",
+               "peak_source": "in-process probe (tools/ubench/probe.cu), this GPU, this run", "kernel": "wf_trace_kernel",
+               "gather_rate_gps": g_rate, "gather_peak_gps": peak_g, "gather_peak_l1_hit_gps": probes_["l1_gather_gps"], "frac_vs_l1_hit_peak": g_rate / probes_["l1_gather_gps"],
+               "sectors_per_traversal": sectors_per_trav, "nodes_per_traversal": cc.nodes / max(cc.traversals, 1), "tris_per_traversal": cc.triangles / max(cc.traversals, 1),
+               "node_bytes": node_bytes, "tri_bytes": tri_bytes, "kernel_ms_per_launch": kernel_s * 1e3, "traversals_per_launch": trav_per_launch,
+               "launches_per_step": t_n / max(steps_, 1), "kernel_share_of_step": (t_ms / max(steps_, 1)) / step_ms,
+               "kernel_mrays_traversed": trav_ / (t_ms * 1e-3) / 1e6,
+               "bounce_launches": {"ms_per_step": (t_ms - p_ms) / max(steps_, 1), "mrays": (rays_ - int(c_.primary_rays)) / max((t_ms - p_ms) * 1e-3, 1e-12) / 1e6},
+               "primary_launches": {"ms_per_step": p_ms / max(steps_, 1), "traversals_per_step": (trav_ - (rays_ - int(c_.primary_rays))) / max(steps_, 1),
+                                    "queries_answered_per_step": int(c_.primary_rays) / max(steps_, 1)}}
+        tr = ncu_traffic(cfg_key)
+        rec["traffic"] = tr.get("dram_bytes_per_launch") if tr else None
+        if tr and tr.get("dram_bytes_per_launch"):
+            per_launch = float(tr["dram_bytes_per_launch"])
+            ach = per_launch / kernel_s / 1e9
+            rec["hbm"] = {"traffic_bytes_per_launch": per_launch, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "source": tr.get("source"),
+                          "dram_bytes_per_traversal": per_launch / trav_per_launch, "record_bytes_requested_per_traversal": 32.0 * sectors_per_trav}
+        return rec
+
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak()
         subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        steps = args.steps
+        step_ms = max_ms / steps
+        roof = kernel_accounting(mat, model, base.sample_count if world == 1 else max(base.sample_count // world, 1), c, steps, step_ms, probes, args.config, peak)
+        if roof is None:      # A/B variants without a separate trace kernel
+            roof = {"bound": "l2", "achieved": None, "peak": probes["l2_gather_gps"] * 32.0, "unit": "GB/s", "frac": None, "traffic": None, "kernel": "render kernel (one launch)"}
         bray, bray_info = oracle_bray(scene, w, h, args.bounces, tile_count=32)
-        # dominant kernel = wf_trace_kernel: every ray passes through exactly one of its launches
         if trace_launches:
-            rays_per_launch = rays / trace_launches
-            kernel_s = trace_ms * 1e-3 / trace_launches   # average launch duration, CUDA events on the launching stream, timed region
-            kname = "wf_trace_kernel"
-        else:                                              # A/B variants without a separate trace kernel: the whole render
-            rays_per_launch = rays / max(args.steps, 1)
-            kernel_s = kernel_ms * 1e-3 / max(args.steps, 1)
-            kname = "render kernel"
-        achieved = bray * rays_per_launch / kernel_s / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        # what the kernel itself requests: its node/triangle counters on one 1-spp pass (untimed, counting build of the kernel)
-        cp = vcrt.render_params(shader="full", traversal=args.traversal, rng="philox", accum="f32", trig="libm", max_bounces=args.bounces,
-                                stack_depth=64, sample_begin=0, sample_count=1, philox_seed=args.scene_seed, flags=vcrt.FLAG_COUNT_TRAVERSAL)
-        mat.clearAccum(); mat.resetCounters()
-        model.renderCommand(None, 0, cp)
-        cc = mat.counters()
-        node_bytes = 32 if mat.getInfo("fast_nodes") == "q15" else 64
-        tri_bytes = 64                                  # the traversal's triangle record (two 256-bit loads per test)
-        own_bray = (node_bytes * cc.nodes + tri_bytes * cc.triangles) / max(cc.rays, 1)
-        # the memory-side ceiling that actually binds the kernel: 32-byte gathers through L1TEX;
-        # peak = dependent random 32-byte gathers missing L1, tools/ubench/gather_tex.cu on this GPU model (profiles/r01_v10_gather_tex_ubench.log)
-        gathers_per_ray = (node_bytes // 32) * cc.nodes / max(cc.rays, 1) + 2.0 * cc.triangles / max(cc.rays, 1) + 1.0
-        g_rate = gathers_per_ray * rays_per_launch / kernel_s / 1e9
-        own = {"own_bytes_per_ray": own_bray, "own_nodes_per_ray": cc.nodes / max(cc.rays, 1), "own_tris_per_ray": cc.triangles / max(cc.rays, 1),
-               "own_node_bytes": node_bytes, "own_tri_bytes": tri_bytes, "own_achieved": own_bray * rays_per_launch / kernel_s / 1e9,
-               "own_frac": own_bray * rays_per_launch / kernel_s / 1e9 / peak,
-               "l1_gather": {"gathers_per_ray": gathers_per_ray, "achieved": g_rate, "peak": L1_GATHER_PEAK_G, "unit": "G 32-byte gathers/s",
-                             "frac": g_rate / L1_GATHER_PEAK_G, "peak_source": "tools/ubench/gather_tex.cu, L1-missing chains, B200"}}
+            ach_c = bray * (rays / trace_launches) / (trace_ms * 1e-3 / trace_launches) / 1e9
+            roof["canonical"] = {"bytes_per_ray": bray, "achieved": ach_c, "peak": peak, "unit": "GB/s", "frac": ach_c / peak, "peak_source": peak_src,
+                                 "note": "SURVEY 8d's figure, kept for the record: 48 B x fetches of the reference-order t-culled traversal of the bound median-split tree, per "
+                                         "closest-hit query; the kernel walks its own 4-wide SAH tree (and bounce 0 once per pixel), so this is not a ceiling", **bray_info}
+        roof["probes"] = probes
+        prim_q, bounce_q = total_prim, total_rays - total_prim
+        cfg = workload_config(args, scene)
+        cfg["implementation"] = "Philox RNG, f32 accumulation, fast traversal (4-wide quantised SAH tree rebuilt over the bound leaves), wavefront pipeline; bounce 0 traced once per pixel"
         line = {"metric": "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, scene), "clocks": clocks, "gpu_launches": total_launches,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "peak_source": peak_src, "kernel": kname, "bytes_per_ray": bray, "roofline_mrays": peak * 1e3 / bray,
-                             "kernel_ms_per_launch": kernel_s * 1e3, "rays_per_launch": rays_per_launch, "launches_per_step": trace_launches / max(args.steps, 1),
-                             "kernel_share_of_step": (trace_ms / max(args.steps, 1)) / (max_ms / args.steps) if trace_launches else 1.0,
-                             "kernel_mrays": rays_per_launch / kernel_s / 1e6, "canonical_traversal": bray_info, **own},
-                "rays_per_step": total_rays / args.steps, "scene_build_s": gen_s}
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "clocks": clocks, "gpu_launches": total_launches,
+                "roofline": roof, "rays_per_step": total_rays / steps, "traversals_per_step": total_trav / steps,
+                "primary_queries_per_step": prim_q / steps, "bounce_rays_per_step": bounce_q / steps,
+                "bounce_mrays": roof.get("bounce_launches", {}).get("mrays"), "primary_mrays": (prim_q / steps / world) / max(roof.get("primary_launches", {}).get("ms_per_step", 0.0) * 1e-3, 1e-12) / 1e6
+                if roof.get("primary_launches") else None,
+                "scene_build_s": gen_s}
+        if frame_check:
+            line.update(frame_check)
+        if strong:
+            line["strong"] = strong
         if e2e:
             line["e2e"] = e2e
+
+    # ---- C4 on one GPU (N=1, default config only): the configuration whose traversal records (0.8 GB) do NOT fit L2, i.e. the
+    # one where HBM can bind.  Same kernel, same accounting, at 1080p / 8 spp (the trace kernel's behaviour per ray does not depend
+    # on the image size; BASELINE's 4K 16-spp frame of this scene is the 8-GPU tile-sharded job).
+    if world == 1 and rank == 0 and args.config == "c3" and not args.no_c4 and not args.static_kernel:
+        try:
+            mat.destroy()
+            del flush
+            torch.cuda.empty_cache()
+            sc4, gen4 = build_workload(args, "c3", triangles=10000000)
+            ubo4, target4, mat4, model4 = make_host_object(sc4, 1920, 1080)
+            mat4.setStream(stream.cuda_stream)
+            p4 = params_for(8)
+            pr4 = dict(probes)
+            pr = Probe(local_rank)
+            dram_gather = pr.gather(26, steps=32)        # 2 GB table: DRAM-resident
+            flush4 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+            def step4():
+                mat4.clearAccum(); model4.renderCommand(None, 0, p4); mat4.resolve(8, 0.0)
+            for _ in range(3):
+                step4()
+            torch.cuda.synchronize()
+            mat4.resetCounters()
+            evs = []
+            for _ in range(3):
+                flush4.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); step4(); e1.record(stream)
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            ms4 = sum(a.elapsed_time(b) for a, b in evs) / 3
+            c4 = mat4.counters()
+            roof4 = kernel_accounting(mat4, model4, 8, c4, 3, ms4, pr4, "c4", peak)
+            roof4["dram_gather_peak_gps"] = dram_gather
+            roof4["frac_vs_dram_gather_peak"] = roof4["gather_rate_gps"] / dram_gather if dram_gather else None
+            if roof4.get("hbm"):
+                roof4["hbm"]["dram_sector_rate_gps"] = roof4["hbm"]["achieved"] / 32.0
+                roof4["hbm"]["frac_vs_dram_gather_peak"] = roof4["hbm"]["achieved"] / 32.0 / dram_gather if dram_gather else None
+            line["c4"] = {"workload": "synthetic %d-triangle lit box (seed %d), 1920x1080, 8 spp, depth 8, one GPU" % (len(sc4["triangles"]) // 48, args.scene_seed),
+                          "fast_nodes": mat4.getInfo("fast_nodes"), "record_bytes": int(mat4.getInfo("fast_node_count")) * 64 + (len(sc4["triangles"]) // 48) * 64,
+                          "value": c4.rays / 3 / (ms4 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms4, "roofline": roof4, "scene_build_s": gen4}
+            mat4.destroy()
+        except Exception as ex:      # the extra leg must never take the headline down with it
+            line["c4"] = {"error": repr(ex)}
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline and args.config in ("c2", "c3"):
+            set_host_threads(os.cpu_count() or 1)
             dt1, rays1, kind = cpu_reference_step(scene, w, h, args.bounces, 1)
             frames = int(min(max(round(15.0 / max(dt1, 1e-3)), 1), 16))
             dt, r, kind = cpu_reference_step(scene, w, h, args.bounces, frames, first_sample=1)
@@ -470,6 +686,8 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if group is not None:
+            group.close()
         dist.destroy_process_group()
 
 

@@ -1,6 +1,9 @@
 // headless_main.cpp -- the reference's application (src/main.cpp) without the window: same scene set-up calls
 // (initScene, main.cpp:76-153), same per-frame protocol (updateScene :166-183, computeCommand :228), rendering to a PPM
-// instead of a swapchain.  Usage: headless_main scene.vcrt out.ppm [frames=16] [width=800] [height=600] [simple]
+// instead of a swapchain.  Usage: headless_main scene.vcrt out.ppm [frames=16] [width=800] [height=600] [simple|full] [gpus=1]
+// With gpus given, the same frames (samples 0..frames-1, f32 accumulation, Philox RNG, fast traversal) are rendered as ONE call
+// sharded over that many GPUs by 32x32 tiles (vcrt_group_*: NCCL all-gather of the packed tiles inside the library); gpus=1
+// takes the same code path on one GPU, and the two outputs are bit-identical.
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -39,6 +42,44 @@ int main(int argc, char** argv) {
         const bool simple = argc > 6 && !strcmp(argv[6], "simple");
         const uint32_t descriptorSetsSize = 1;   // swapchain image count in the reference
         auto rtScene = std::make_shared<RtScene>(argv[1]);
+        if (argc > 7) {   // ---- multi-GPU leg: the scene set-up calls of initScene once per GPU, through the group
+            const int gpus = atoi(argv[7]);
+            vcrt_group* group = nullptr;
+            auto gcheck = [&](int rc) { if (rc != VCRT_OK) throw std::runtime_error(vcrt_group_last_error(group)); };
+            gcheck(vcrt_group_create_local(gpus, nullptr, &group));
+            gcheck(vcrt_group_set_shader(group, simple ? "ray-trace-compute-simple" : "ray-trace-compute"));
+            gcheck(vcrt_group_set_image_size(group, W, H));
+            gcheck(vcrt_group_set_buffer(group, VCRT_BINDING_TRIANGLES, rtScene->triangles.data(), rtScene->triangles.size() * sizeof(vcrt_triangle)));
+            gcheck(vcrt_group_set_buffer(group, VCRT_BINDING_MATERIALS, rtScene->materials.data(), rtScene->materials.size() * sizeof(vcrt_material)));
+            gcheck(vcrt_group_set_buffer(group, VCRT_BINDING_BVH, rtScene->bvhNodes.data(), rtScene->bvhNodes.size() * sizeof(vcrt_bvh_node)));
+            gcheck(vcrt_group_set_buffer(group, VCRT_BINDING_LIGHTS, rtScene->lights.data(), rtScene->lights.size() * sizeof(vcrt_light)));
+            gcheck(vcrt_group_set_buffer(group, VCRT_BINDING_SPHERES, rtScene->spheres.data(), rtScene->spheres.size() * sizeof(vcrt_sphere)));
+            vcrt_ubo ubo = {{1.8f, 8.6f, 1.1f}, 0.0f, 0u, (uint32_t)rtScene->triangles.size(), (uint32_t)rtScene->lights.size(), (uint32_t)rtScene->spheres.size()};
+            gcheck(vcrt_group_set_ubo(group, &ubo));
+            vcrt_render_params p;
+            std::memset(&p, 0, sizeof p);
+            p.struct_size = sizeof p;
+            p.shader = simple ? VCRT_SHADER_SIMPLE : VCRT_SHADER_FULL;
+            p.traversal = VCRT_TRAVERSAL_FAST; p.rng_mode = VCRT_RNG_PHILOX; p.accum_mode = VCRT_ACCUM_F32; p.max_bounces = 8;
+            p.sample_count = (uint32_t)frames;
+            gcheck(vcrt_group_render(group, &p, VCRT_SHARD_TILES, 2.2f));   // warm-up: record builds, NCCL channels
+            gcheck(vcrt_group_synchronize(group));
+            auto g0 = std::chrono::steady_clock::now();
+            gcheck(vcrt_group_render(group, &p, VCRT_SHARD_TILES, 2.2f));
+            std::vector<uint8_t> px((size_t)W * H * 4), other((size_t)W * H * 4);
+            gcheck(vcrt_group_read_target_rgba8(group, 0, px.data(), px.size()));
+            double gms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g0).count();
+            for (int i = 1; i < gpus; ++i) {   // tile sharding leaves the complete frame on every GPU
+                gcheck(vcrt_group_read_target_rgba8(group, i, other.data(), other.size()));
+                if (other != px) throw std::runtime_error("failed to gather tiles: GPU " + std::to_string(i) + " holds a different frame");
+            }
+            printf("%f ms/frame (%d samples on %d GPUs, tile-sharded)\n", gms, frames, gpus);
+            std::ofstream gout(argv[2], std::ios::binary);
+            gout << "P6\n" << W << " " << H << "\n255\n";
+            for (size_t i = 0; i < (size_t)W * H; ++i) gout.write((const char*)&px[4 * i], 3);
+            vcrt_group_destroy(group);
+            return EXIT_SUCCESS;
+        }
 
         auto uniformBufferBundle = std::make_shared<BufferBundle>(descriptorSetsSize);
         BufferUtils::createBundle<UniformBufferObject>(uniformBufferBundle.get(), UniformBufferObject(), VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT, VMA_MEMORY_USAGE_CPU_TO_GPU);

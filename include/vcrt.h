@@ -194,6 +194,46 @@ int vcrt_synchronize(vcrt_ctx* ctx);
 int vcrt_get_counters(vcrt_ctx* ctx, vcrt_counters* out);           /* synchronises */
 int vcrt_reset_counters(vcrt_ctx* ctx);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU groups (no reference counterpart: one VkDevice and one queue, VulkanApplicationContext.cpp:95-119; the shader's
+ * invocations never communicate, so pixels and samples partition freely -- SURVEY.md 8e).  The scene is replicated; one call
+ * renders one frame on all GPUs of the group and combines the shares with ONE NCCL collective on the render streams:
+ *   VCRT_SHARD_TILES    32x32 tile k (row-major) is rendered by rank k % world; every rank resolves its tiles to rgba8, the
+ *                       packed tiles are all-gathered and scattered: EVERY rank ends up with the full rgba8 target, bit-identical
+ *                       to a 1-GPU render (both RNG modes are keyed by the pixel)
+ *   VCRT_SHARD_SAMPLES  rank r renders a contiguous slice of the samples of every pixel; the f32 accumulation buffers are
+ *                       sum-reduced onto rank 0, which resolves: RANK 0 ends up with the full target (same sample set as a 1-GPU
+ *                       render; fp32 summation order differs)
+ * Two ways to form a group: one process driving n devices (create_local: the group owns n contexts, the set_* calls below
+ * broadcast to them), or one process per GPU (create_rank: wraps the caller's context; rank 0 obtains an id with
+ * vcrt_group_unique_id and the caller distributes its VCRT_GROUP_ID_BYTES bytes, e.g. through torch.distributed / MPI).
+ * NCCL (libnccl.so.2) is loaded at run time; groups of size 1 need none.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vcrt_group vcrt_group;
+enum { VCRT_SHARD_TILES = 0, VCRT_SHARD_SAMPLES = 1 };
+#define VCRT_GROUP_ID_BYTES 128
+
+int vcrt_group_unique_id(void* id /* VCRT_GROUP_ID_BYTES */);
+int vcrt_group_create_local(int n_devices, const int* devices /* NULL = 0..n-1 */, vcrt_group** out);
+int vcrt_group_create_rank(vcrt_ctx* ctx /* borrowed */, const void* id, int rank, int world, vcrt_group** out);
+int vcrt_group_destroy(vcrt_group* group);                        /* a local group destroys its contexts too */
+const char* vcrt_group_last_error(const vcrt_group* group);       /* group may be NULL: error of the last failed create on this thread */
+int vcrt_group_size(const vcrt_group* group);                     /* ranks in the group */
+int vcrt_group_local_count(const vcrt_group* group);              /* contexts this process drives */
+int vcrt_group_rank(const vcrt_group* group, int local_index);    /* rank of local context i */
+vcrt_ctx* vcrt_group_ctx(vcrt_group* group, int local_index);     /* for per-context calls (options, counters, read-backs) */
+/* the single-context setters, applied to every local context (main.cpp:84-153 once per GPU) */
+int vcrt_group_set_shader(vcrt_group* group, const char* shader_path);
+int vcrt_group_set_buffer(vcrt_group* group, int binding, const void* host, size_t bytes);
+int vcrt_group_set_image_size(vcrt_group* group, uint32_t width, uint32_t height);
+int vcrt_group_set_ubo(vcrt_group* group, const vcrt_ubo* ubo);
+int vcrt_group_set_option(vcrt_group* group, const char* key, const char* value);
+/* One frame: clears the accumulation, renders params (accum_mode must be VCRT_ACCUM_F32; sample_count = the frame's total;
+ * tile_rank/tile_count must be 0) sharded by `mode`, combines, resolves with `gamma` (vcrt_resolve).  Asynchronous. */
+int vcrt_group_render(vcrt_group* group, const vcrt_render_params* params, int mode, float gamma);
+int vcrt_group_read_target_rgba8(vcrt_group* group, int local_index, void* dst, size_t bytes);   /* synchronises that context */
+int vcrt_group_synchronize(vcrt_group* group);
+
 #ifdef __cplusplus
 }
 #endif

@@ -708,6 +708,111 @@ def test_two_gpus_match_one(mode):
         assert dict(out) == {0: True, 1: True}
 
 
+def test_group_api_single_process(oracle, doge, tmp_path):
+    """vcrt_group_* (multi-GPU through the C ABI, NCCL inside the library).  (1) A local group of every GPU of the box -- one on
+    the driver's box, where the path is exercised with world = 1 -- renders the same frame as a plain context, in both sharding
+    modes.  (2) With two or more GPUs: tile shards reproduce the 1-GPU frame bit for bit ON EVERY GPU, sample slices within
+    1 LSB of the resolved rgba8 frame.  (3) The C++ example's multi-GPU leg (examples/headless_main.cpp) writes the same
+    picture for gpus = 1 and gpus = all."""
+    import subprocess
+    import torch
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from vulkan_compute_ray_tracing_b200 import sharding
+    from gpuharness import GpuScene
+    from test_boundary import build_cpp_example
+    w, h, spp = 800, 600, 6
+    p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=4, sample_begin=3, sample_count=spp, philox_seed=5)
+    one = GpuScene(doge, w, h)
+    one.set_camera(CAM, 0)
+    one.material.clearAccum()
+    one.model.renderCommand(None, 0, p)
+    one.material.resolve(spp, 2.2)
+    want = one.target.read()
+    one.close()
+    ubo = vcrt.pack_ubo(CAM, 0, doge)
+    ngpu = torch.cuda.device_count()
+    for n in sorted({1, min(ngpu, 2), ngpu}):
+        g = sharding.LocalGroup(n, doge, w, h)
+        g.render(ubo, p, "tiles", 2.2)
+        for i in range(n):
+            assert np.array_equal(g.read_target(i), want), ("tiles", n, i)
+        g.render(ubo, p, "samples", 2.2)
+        got = g.read_target(0)
+        assert (np.array_equal(got, want) if n == 1 else frac_within_1lsb(got, want) == 1.0), ("samples", n)
+        with pytest.raises(vcrt.VcrtError, match="f32 accumulation"):
+            g.render(ubo, vcrt.render_params(accum="rgba8_ref"), "tiles")
+        g.close()
+    exe = build_cpp_example(tmp_path / "headless_main")
+    scene_path = os.path.join(GOLDEN, "doge_scene.vcrt")
+    outs = []
+    for n in sorted({1, ngpu}):
+        r = subprocess.run([exe, scene_path, str(tmp_path / ("g%d.ppm" % n)), "4", "320", "200", "full", str(n)], capture_output=True, text=True)
+        assert r.returncode == 0 and "tile-sharded" in r.stdout, r.stderr
+        outs.append((tmp_path / ("g%d.ppm" % n)).read_bytes())
+    assert all(o == outs[0] for o in outs) and len(outs[0]) == len(b"P6\n320 200\n255\n") + 320 * 200 * 3
+
+
+def _group_rank_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import vulkan_compute_ray_tracing_b200 as vcrt
+        from vulkan_compute_ray_tracing_b200 import sharding
+        from gpuharness import GpuScene
+        from refharness import load_scene
+        scene = load_scene(os.path.join(GOLDEN, "doge_scene.vcrt"))
+        w, h, spp = 800, 600, 5
+        g = GpuScene(scene, w, h, device=rank)
+        grp = sharding.Group.from_torch(g.material)
+        base = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=4, sample_count=spp, philox_seed=9)
+        g.set_camera(CAM, 0)
+        ok = True
+        for mode in ("tiles", "samples"):
+            grp.render(g.model, base, mode, 0.0)
+            got = g.target.read()
+            g.material.clearAccum()
+            g.model.renderCommand(None, 0, base)
+            g.material.resolve(spp, 0.0)
+            want = g.target.read()
+            if mode == "tiles":
+                ok = ok and bool(np.array_equal(got, want))
+            elif rank == 0:
+                ok = ok and bool((np.abs(got.astype(int) - want.astype(int)) <= 1).all())
+        out[rank] = ok
+        grp.close()
+        g.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_group_api_one_process_per_gpu():
+    """vcrt_group_create_rank under a torchrun-style launch (one process per GPU, the NCCL id carried by torch.distributed):
+    the tile-sharded frame is bit-identical to the 1-GPU frame on every rank, sample slices within 1 LSB on rank 0."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        procs = [ctx.Process(target=_group_rank_worker, args=(r, 2, port, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=300)
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+            assert p.exitcode == 0
+        assert dict(out) == {0: True, 1: True}
+
+
 def test_post_process_matches_oracle(gpu_doge, oracle):
     """vcrt_post_process (CUDA) vs the restated fragment shader: gamma-only exactly as shipped, and with smartDeNoise enabled
     as its commented-out call would (mix 0.5, sigma 2, kSigma 2, threshold 0.05).  expf/powf differ by ulps between CUDA and

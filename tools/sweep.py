@@ -18,10 +18,12 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--count", action="store_true")
 ap.add_argument("--trace", action="store_true", help="also print the trace kernel's own time")
 ap.add_argument("--flags", type=int, default=0, help="8 static kernel, 16 megakernel")
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("opts", nargs="*")
 a = ap.parse_args()
 scene = scenegen.generate_box_scene(a.triangles, seed=1234)
-w, h = 1920, 1080
+w, h = a.width, a.height
 ubo = vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), vcrt.pack_ubo(vcrt.CAMERA_START, 0, scene))
 m = vcrt.ComputeMaterial("ray-trace-compute.spv")
 m.addUniformBufferBundle(ubo)
@@ -45,5 +47,7 @@ for combo in itertools.product(*vals) if vals else [()]:
             best = max(best, c.rays / c.kernel_ms / 1e3)
     extra = " nodes/ray %.1f tris/ray %.2f" % (c.nodes / c.rays, c.triangles / c.rays) if a.count else ""
     if a.trace:
-        extra += " trace %.2f ms in %d launches = %.0f Mrays/s" % (c.trace_ms, c.trace_launches, c.rays / max(c.trace_ms, 1e-9) / 1e3)
+        bounce_ms = c.trace_ms - c.primary_trace_ms
+        extra += " trace %.2f ms in %d launches; bounce launches %.2f ms = %.0f Mrays/s; primary launches %.3f ms" % (
+            c.trace_ms, c.trace_launches, bounce_ms, (c.rays - c.primary_rays) / max(bounce_ms, 1e-9) / 1e3, c.primary_trace_ms)
     print(dict(zip(keys, combo)), "%.0f Mrays/s (best of %d, %.1f ms)%s" % (best, a.reps, c.kernel_ms, extra), flush=True)

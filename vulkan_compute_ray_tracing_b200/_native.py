@@ -65,6 +65,23 @@ SIGNATURES = {
     "vcrt_synchronize": (C.c_int, [_P]),
     "vcrt_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "vcrt_reset_counters": (C.c_int, [_P]),
+    "vcrt_group_unique_id": (C.c_int, [_P]),
+    "vcrt_group_create_local": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
+    "vcrt_group_create_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vcrt_group_destroy": (C.c_int, [_P]),
+    "vcrt_group_last_error": (C.c_char_p, [_P]),
+    "vcrt_group_size": (C.c_int, [_P]),
+    "vcrt_group_local_count": (C.c_int, [_P]),
+    "vcrt_group_rank": (C.c_int, [_P, C.c_int]),
+    "vcrt_group_ctx": (_P, [_P, C.c_int]),
+    "vcrt_group_set_shader": (C.c_int, [_P, C.c_char_p]),
+    "vcrt_group_set_buffer": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "vcrt_group_set_image_size": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "vcrt_group_set_ubo": (C.c_int, [_P, C.POINTER(Ubo)]),
+    "vcrt_group_set_option": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
+    "vcrt_group_render": (C.c_int, [_P, C.POINTER(RenderParams), C.c_int, C.c_float]),
+    "vcrt_group_read_target_rgba8": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "vcrt_group_synchronize": (C.c_int, [_P]),
 }
 
 _lib = None

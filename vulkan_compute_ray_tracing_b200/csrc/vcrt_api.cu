@@ -10,65 +10,12 @@
 #include <vector>
 
 #include "../../include/vcrt.h"
+#include "vcrt_ctx.h"
 #include "vcrt_host_setup.h"
 #include "vcrt_launch.h"
 #include "vcrt_repack.h"
 
 using namespace vcrt;
-
-struct DevBuf {
-    void* ptr = nullptr;
-    size_t bytes = 0;      // bytes in use
-    size_t capacity = 0;
-};
-
-struct vcrt_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t own_stream = nullptr;
-    std::string error;
-    int shader = VCRT_SHADER_FULL;
-    DevBuf ssbo[8];                       // bindings 3..7 in the reference's layouts
-    std::vector<uint8_t> host_tris, host_bvh;  // shadows for the repack
-    bool fast_dirty = true;
-    uint32_t continue_threshold = 20;   // option "continue_threshold" (33 - min(leaf, shade) leaves the schedule unchanged)
-    uint32_t leaf_threshold = 6, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
-    bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
-    int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (4-wide quantised when the scene extent allows) | 1 "q15" (binary) | 2 "f32" | 3 "q15x4"
-    bool quantized = false, wide = false;
-    int32_t froot4 = (int32_t)0x80000000;
-    uint32_t nf4nodes = 0;
-    DevBuf q4nodes;
-    float qorg[3] = {0, 0, 0}, qext[3] = {0, 0, 0};
-    DevBuf qnodes;
-    uint32_t fast_depth = 0, bound_depth = 0;
-    int dispatch_trav = 0;                // option "dispatch_traversal": 0 "auto" | 1 "reference" | 2 "fast"
-    bool dispatch_fast = false;           // what the last vcrt_dispatch walked
-    bool fast_ok = false;
-    std::string fast_err;
-    DevBuf fnodes, ftris;
-    DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues (all pipelines' sets, back to back)
-    uint32_t wf_capacity = 0;              // paths per queue set
-    int wf_sets = 0;                       // queue sets the buffers are currently carved into
-    int wf_streams = 0;                    // option "wf_streams": 0 "auto" | 1..VCRT_MAX_PIPES pipelines of a wavefront render
-    cudaStream_t pipe_stream[VCRT_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (the render stream)
-    cudaEvent_t fork_ev = nullptr, join_ev[VCRT_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> ev_pool;      // timing events of finished renders, reused
-    uint32_t wf_batch = 256u << 20;        // option "wf_batch_paths": paths per wavefront batch (queue memory = 120 B per path, allocated for what a call needs).
-                                           // Every trace launch ends in a ~110 us tail (the longest rays): C3 at 64 spp, 32 Mi / 64 Mi / one batch: 5395 / 5620 / 5763 Mrays/s
-    int32_t froot = (int32_t)0x80000000;
-    uint32_t nfnodes = 0;
-    uint32_t W = 0, H = 0;
-    DevBuf target, accum8, accumf, aov, present;
-    vcrt_ubo ubo;
-    unsigned long long* d_counters = nullptr;   // [0] queries [1] nodes [2] tris [3] work counter [4] traversals [5] bounce-0 queries (vcrt_kernels.inl: flush_stats)
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
-    double kernel_ms = 0.0;
-    uint64_t launches = 0;
-    TraceTimer trace_timer;
-    double trace_ms = 0.0;
-    uint64_t trace_launches = 0;
-};
 
 static thread_local std::string g_create_error;
 
@@ -89,6 +36,11 @@ static int cuda_fail(vcrt_ctx* c, cudaError_t e, const char* what) {
     return fail(c, VCRT_ERR_CUDA, std::string("failed to ") + what + ": " + cudaGetErrorString(e));
 }
 #define CU(c, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, (what)); } while (0)
+
+int vcrt_fail(vcrt_ctx* c, int code, const std::string& msg) { return fail(c, code, msg); }
+int vcrt_cuda_fail(vcrt_ctx* c, cudaError_t e, const char* what) { return cuda_fail(c, e, what); }
+static int ensure(vcrt_ctx* c, DevBuf& b, size_t bytes, const char* what);
+int vcrt_ensure(vcrt_ctx* c, DevBuf& b, size_t bytes, const char* what) { return ensure(c, b, bytes, what); }
 
 static int ensure(vcrt_ctx* c, DevBuf& b, size_t bytes, const char* what) {
     if (bytes > b.capacity) {

@@ -237,11 +237,21 @@ __device__ __forceinline__ void trav_descend(TravState& t, float lN, float rN, b
 // The stack side of a 4-wide visit.  c[] as returned by trav_test4.  The nearest child, when it is a leaf and nothing is
 // parked yet, goes into `pending`; of the remaining k children the nearest becomes the node, the others go onto the stack
 // farthest first (the old top moves to memory, the second nearest becomes the new top).
-__device__ __forceinline__ void trav_descend4(TravState& t, int32_t c[4], int32_t& pending, int32_t& tos, const StackRef& sr) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void trav_descend4(TravState& t, const SceneView& s, int32_t c[4], int32_t& pending, int32_t& tos, const StackRef& sr) {
     const bool park = c[0] != VCRT_FAST_EMPTY && c[0] < 0 && pending == VCRT_FAST_EMPTY;
+#if VCRT_PF_L2
+    // Working sets beyond L2 (the 10 M-triangle scene): records that will be needed a few iterations from now -- the leaf just
+    // parked and the child that becomes the top of the stack -- are pulled into L2 now, so that their DRAM latency overlaps the
+    // visits in between instead of stalling the lane's warp when its turn comes (no register, no L1 allocation).
+    if (park) prefetch_l2(s.ftris + 4 * (size_t)(~c[0]));
+#endif
     pending = park ? c[0] : pending;
     c[0] = park ? c[1] : c[0]; c[1] = park ? c[2] : c[1]; c[2] = park ? c[3] : c[2]; c[3] = park ? VCRT_FAST_EMPTY : c[3];
     const bool k1 = c[0] != VCRT_FAST_EMPTY, k2 = c[1] != VCRT_FAST_EMPTY, k3 = c[2] != VCRT_FAST_EMPTY, k4 = c[3] != VCRT_FAST_EMPTY;
+#if VCRT_PF_L2
+    if (k2) prefetch_l2(c[1] >= 0 ? (const void*)(s.q4nodes + 2 * (size_t)c[1]) : (const void*)(s.ftris + 4 * (size_t)(~c[1])));
+#endif
     sr.store_if(k2, t.sp, tos);
     sr.store_if(k3, t.sp + 1, k4 ? c[3] : c[2]);
     sr.store_if(k4, t.sp + 2, c[2]);

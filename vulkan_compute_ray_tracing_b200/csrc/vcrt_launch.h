@@ -83,6 +83,7 @@ cudaError_t launch_render_reference(const KernelArgs& a, int shader, int rng, in
 cudaError_t launch_render_fast(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_render_brute(const KernelArgs& a, int shader, int rng, int trig, bool count, cudaStream_t stream);
 cudaError_t launch_tiles(void* image, void* packed, int elem_bytes, bool pack, uint32_t W, uint32_t H, uint32_t rank, uint32_t count, uint32_t owned, cudaStream_t stream);
+cudaError_t launch_unpack_all_tiles(void* image, const void* gathered, int elem_bytes, uint32_t W, uint32_t H, uint32_t world, uint32_t tiles_per_rank, cudaStream_t stream);
 cudaError_t launch_post_process(const uchar4* tex, uchar4* out, uint32_t w, uint32_t h, float mix, float sigma, float kSigma, float threshold, float inv_gamma,
                                 cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accumf, uchar4* target, uint32_t npix, float inv_total, float inv_gamma, cudaStream_t stream);

@@ -55,6 +55,26 @@ cudaError_t launch_tiles(void* image, void* packed, int elem_bytes, bool pack, u
     return cudaGetLastError();
 }
 
+// All peers' tiles at once (vcrt_group_render): `gathered` = the packed buffers of ranks 0..world-1 back to back, each
+// tiles_per_rank * 1024 elements (padded); one thread per image pixel fetches its value from the owner's buffer.
+template <typename T>
+__global__ void unpack_all_tiles_kernel(T* __restrict__ image, const T* __restrict__ gathered, uint32_t W, uint32_t H, uint32_t tilesX, uint32_t world, uint32_t tiles_per_rank) {
+    const uint32_t x = blockIdx.x * 32u + (threadIdx.x & 31u), y = blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const uint32_t tile = (y >> 5) * tilesX + (x >> 5);
+    const uint32_t rank = tile % world, j = tile / world;
+    image[(size_t)y * W + x] = gathered[((size_t)rank * tiles_per_rank + j) * 1024u + ((y & 31u) << 5) + (x & 31u)];
+}
+
+cudaError_t launch_unpack_all_tiles(void* image, const void* gathered, int elem_bytes, uint32_t W, uint32_t H, uint32_t world, uint32_t tiles_per_rank, cudaStream_t stream) {
+    if (W == 0 || H == 0 || world == 0) return cudaSuccess;
+    const dim3 grid((W + 31) / 32, (H + 7) / 8);
+    const uint32_t tilesX = (W + 31) / 32;
+    if (elem_bytes == 4) unpack_all_tiles_kernel<uchar4><<<grid, 256, 0, stream>>>((uchar4*)image, (const uchar4*)gathered, W, H, tilesX, world, tiles_per_rank);
+    else unpack_all_tiles_kernel<float4><<<grid, 256, 0, stream>>>((float4*)image, (const float4*)gathered, W, H, tilesX, world, tiles_per_rank);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------- post-process pass
 // post-process-shader.frag:26-70 on the rgba8 target: smartDeNoise (a bilateral filter over a disc of radius
 // round(kSigma*sigma); the shader ships with it commented out of main, :64) blended with the plain texel by `mix`, then

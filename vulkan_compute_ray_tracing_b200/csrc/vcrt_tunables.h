@@ -30,6 +30,9 @@
 #ifndef VCRT_SHADE_GRID
 #define VCRT_SHADE_GRID 8u /* shade kernel: blocks per SM in the grid-stride launch (8 vs 20: no difference) */
 #endif
+#ifndef VCRT_PF_L2
+#define VCRT_PF_L2 0     /* trace kernel, 4-wide nodes: prefetch.global.L2 of the parked leaf's triangle and of the new top-of-stack child (A/B for HBM-sized scenes) */
+#endif
 #ifndef VCRT_PREFETCH
 #define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
 #endif

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                         const Words8 na = ldg8(p), nb = ldg8(p + 1);
                         int32_t c[4];
                         trav_test4(t, na, nb, c);
-                        trav_descend4(t, c, pending, tos, sr);
+                        trav_descend4(t, s, c, pending, tos, sr);
                     }
                 } else if (t.node >= 0) {
                     if (COUNT) st.nodes++;

@@ -13,8 +13,10 @@ partition freely.  Two partitions, both expressed through fields of vcrt_render_
              reduce.  The sample set equals the 1-GPU run's (seeds depend on the global sample index, random.glsl:19 /
              the Philox counter); only the fp32 summation order differs.
 
-This module is host logic + torch.distributed plumbing (NCCL on the GPUs, gloo in the CPU tests); rendering happens in
-the CUDA library through the `render` callable the caller supplies.
+On the GPUs the partition AND the exchange live in the C ABI (include/vcrt.h: vcrt_group_*, NCCL inside libvcrt.so on the
+render streams); `Group` / `LocalGroup` below are thin callers.  torch.distributed only carries the 128-byte NCCL id between
+the processes of a torchrun launch.  The pure-host functions (tile/sample partition, packed-tile layout, `render_sharded`
+over any torch.distributed backend) define the same partition for the gloo CPU tests and for checking the kernels.
 """
 import copy
 
@@ -135,3 +137,97 @@ def render_sharded(render, params, mode, rank, world, total_samples=None, group=
     if world > 1:
         reduce_accumulation(accum, group=group, dst=dst)
     return accum
+
+
+MODES = {"tiles": 0, "samples": 1}     # VCRT_SHARD_TILES / VCRT_SHARD_SAMPLES
+
+
+class Group:
+    """One process per GPU (torchrun): vcrt_group_create_rank around this process's ComputeMaterial.  `render` = one frame on
+    all GPUs: this rank's share + ONE NCCL collective inside libvcrt.so on the render stream + resolve."""
+
+    def __init__(self, material, rank, world, id_bytes=None):
+        import ctypes as C
+        from . import _native as N
+        material.init()
+        self.material, self.rank, self.world = material, rank, world
+        self._g = C.c_void_p()
+        L = N.lib()
+        buf = C.create_string_buffer(bytes(id_bytes), 128) if id_bytes is not None else None
+        if L.vcrt_group_create_rank(material._ctx, buf, rank, world, C.byref(self._g)) != 0:
+            raise N.VcrtError(L.vcrt_group_last_error(None).decode())
+
+    @staticmethod
+    def unique_id():
+        import ctypes as C
+        from . import _native as N
+        buf = C.create_string_buffer(128)
+        if N.lib().vcrt_group_unique_id(buf) != 0:
+            raise N.VcrtError(N.lib().vcrt_group_last_error(None).decode())
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, material, group=None):
+        """Rank 0 creates the NCCL id; torch.distributed (any backend) hands it to the other ranks."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 and world > 1 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        return cls(material, rank, world, box[0])
+
+    def render(self, model, params, mode, gamma=0.0, currentFrame=0):
+        import ctypes as C
+        from . import _native as N
+        model.getMaterial().bind(None, currentFrame)        # the frame's UBO, as computeCommand does
+        if N.lib().vcrt_group_render(self._g, C.byref(params), MODES[mode], float(gamma)) != 0:
+            raise N.VcrtError(N.lib().vcrt_group_last_error(self._g).decode())
+
+    def close(self):
+        from . import _native as N
+        if self._g is not None:
+            N.lib().vcrt_group_destroy(self._g)
+            self._g = None
+
+
+class LocalGroup:
+    """One process driving n GPUs: vcrt_group_create_local; the scene goes to every GPU through the group's setters."""
+
+    def __init__(self, n_devices, scene, width, height, shader="ray-trace-compute", devices=None):
+        import ctypes as C
+        from . import _native as N
+        L = N.lib()
+        self._g = C.c_void_p()
+        devs = (C.c_int * n_devices)(*devices) if devices is not None else None
+        if L.vcrt_group_create_local(n_devices, devs, C.byref(self._g)) != 0:
+            raise N.VcrtError(L.vcrt_group_last_error(None).decode())
+        self.n, self.width, self.height = n_devices, width, height
+        self._check(L.vcrt_group_set_shader(self._g, shader.encode()))
+        self._check(L.vcrt_group_set_image_size(self._g, width, height))
+        for i, name in enumerate(("triangles", "materials", "bvh", "lights", "spheres")):
+            a = np.ascontiguousarray(scene[name]).view(np.uint8).reshape(-1)
+            self._check(L.vcrt_group_set_buffer(self._g, 3 + i, a.ctypes.data if a.nbytes else None, a.nbytes))
+
+    def _check(self, rc):
+        from . import _native as N
+        if rc != 0:
+            raise N.VcrtError(N.lib().vcrt_group_last_error(self._g).decode())
+
+    def render(self, ubo_bytes, params, mode, gamma=0.0):
+        import ctypes as C
+        from . import _native as N
+        ubo = N.Ubo.from_buffer_copy(bytes(ubo_bytes))
+        self._check(N.lib().vcrt_group_set_ubo(self._g, C.byref(ubo)))
+        self._check(N.lib().vcrt_group_render(self._g, C.byref(params), MODES[mode], float(gamma)))
+
+    def read_target(self, local_index=0):
+        from . import _native as N
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        self._check(N.lib().vcrt_group_read_target_rgba8(self._g, local_index, out.ctypes.data, out.nbytes))
+        return out
+
+    def close(self):
+        from . import _native as N
+        if self._g is not None:
+            N.lib().vcrt_group_destroy(self._g)
+            self._g = None
