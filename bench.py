@@ -544,15 +544,19 @@ def main():
                 return 1e3 * dt / nfr, mat.counters().rays / dt / 1e6
             nfr = 64
             ms1, v1 = frame_loop(nfr)
-            e2e["frame_1spp"] = {"ms_per_frame": ms1, "value": v1, "unit": "Mrays/s", "frames": nfr, "wf_streams": "auto (4 parallel pipelines)",
+            e2e["frame_1spp"] = {"ms_per_frame": ms1, "value": v1, "unit": "Mrays/s", "frames": nfr,
                                  "protocol": "progressive frame loop, one sample per frame, rgba8 frame read back every frame"}
-            mat.setOption("wf_streams", "1")
-            ms1s, _ = frame_loop(nfr)
-            mat.setOption("wf_streams", "auto")
-            e2e["frame_1spp"]["ms_per_frame_one_pipeline"] = ms1s
+        # a scene change every step: the records are rebuilt on the device (fast_build=device: CUDA kernels over the uploaded buffers);
+        # `host_build` = the same with the host builder (binned SAH on the CPU cores + upload of its records)
+        mat.setOption("fast_build", "device")
         v, ms = timed(True, min(args.steps, 3))
         e2e["with_scene_upload"] = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
-                                    "includes": "upload of the 5 scene buffers from pinned host memory + rebuild of the traversal records, every step"}
+                                    "record_build": mat.getInfo("fast_build"), "record_build_ms": float(mat.getInfo("fast_build_ms")),
+                                    "includes": "upload of the 5 scene buffers from pinned host memory + rebuild of the traversal records on the device, every step"}
+        mat.setOption("fast_build", "host")
+        v, ms = timed(True, min(args.steps, 2))
+        e2e["with_scene_upload"]["host_build"] = {"value": v, "ms_per_step": ms, "record_build_ms": float(mat.getInfo("fast_build_ms"))}
+        mat.setOption("fast_build", "auto")
 
     def kernel_accounting(mat_, model_, spp_, c_, steps_, step_ms, probes_, cfg_key, hbm_peak):
         """Roofline records of the dominant kernel from live counters: c_ = counters of the timed region (steps of spp_ samples)."""

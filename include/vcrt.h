@@ -173,17 +173,20 @@ int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile
 /* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
  * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
  * (default: 4-wide quantised 64-byte nodes when the scene extent allows, else binary 64-byte float nodes), "q15x4" (4-wide quantised
- * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "dispatch_traversal": what vcrt_dispatch walks -- "auto" (default: the fast tree whenever
+ * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "fast_build": where the records are built -- "auto" (default: on the
+ * device, by CUDA kernels reading the bound buffers where they lie, whenever the default tree is wanted (fast_bvh=sah with fast_nodes=auto|q15x4)
+ * and the scene allows; else by the host builder), "host", "device" (fail instead of falling back); "dispatch_traversal": what vcrt_dispatch walks -- "auto" (default: the fast tree whenever
  * the bound tree is at most 13 levels deep, i.e. whenever the shader's 16-entry stack cannot overflow; identical frames), "reference" (always the
  * literal hit_bvh), "fast"; "wf_batch_paths":
- *  paths per wavefront batch (queue memory: 120 B per path); "wf_streams": "auto" (default) or 1..4 -- a wavefront render
- * whose work fits several batches runs them as parallel pipelines on that many streams (auto: 4 for renders of 256 Ki..32 Mi paths,
- * e.g. a 1-spp frame, else 1); "trace_timing": "on" (default) | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
+ *  paths per wavefront batch (queue memory: 120 B per path); "wf_streams": "auto" (default, = 1) or 1..4 -- the render is cut
+ * into that many batches, run as parallel pipelines on separate streams with their own queue sets (an A/B knob: measured
+ * slower than one pipeline on a 1-spp frame); "trace_timing": "on" (default) | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
  * "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 
 /* Read-only facts about ctx as text: "fast_nodes" -> "q15x4" | "q15" | "f32" | "none" (what the fast traversal walks after the last
- * upload), "fast_node_count", "fast_depth", "wf_batch_paths", "dispatch_kernel" ("fast" | "reference": what the last vcrt_dispatch walked), "device".  Builds the fast records if they are stale. */
+ * upload), "fast_node_count", "fast_depth", "wf_batch_paths", "dispatch_kernel" ("fast" | "reference": what the last vcrt_dispatch walked), "fast_build" ("device" | "host": where the current records were
+ * built), "fast_build_ms" (wall time of that build), "device".  Builds the fast records if they are stale. */
 int vcrt_get_info(vcrt_ctx* ctx, const char* key, char* value, size_t capacity);
 
 /* Run ctx's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores ctx's own stream), so

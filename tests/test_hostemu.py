@@ -119,6 +119,50 @@ def test_deep_bound_tree_is_fine_once_rebuilt(oracle, hostemu):
         hostemu.render(sc, (0.0, 6.0, 1.5), 64, 48, p)
 
 
+def test_device_build_algorithm(oracle, hostemu, doge):
+    """The on-device record build (vcrt_devbuild.cuh: tie ranks by counting, PLOC topology, level-by-level 4-wide collapse) run
+    sequentially on the CPU through the same per-element code: every bit equals the reference traversal's, on the bundled
+    scene, on tiny trees, on duplicated triangles (ties), on trees with one-child / childless inner nodes, and with forced
+    quantisation of a scene 1000x larger than the automatic limit."""
+    import tinybvh
+    cases = [(doge, CAM, 160, 120, 16)]
+    for seed, n in ((51, 1), (52, 2), (53, 3), (54, 5), (55, 40), (56, 700), (57, 4000)):
+        cases.append((small_scene(n_tris=n, seed=seed), (0.0, 6.0, 1.5), 96, 64, 16))
+    dup = dict(small_scene(n_tris=60, seed=58))
+    tri = dup["triangles"].reshape(-1, 48)
+    dup["triangles"] = np.concatenate([tri, tri]).reshape(-1).copy()
+    dup["bvh"] = tinybvh.build_bvh(dup["triangles"].view(tinybvh.TRI), seed=6).view(np.uint8).reshape(-1).copy()
+    cases.append((dup, (0.0, 6.0, 1.5), 96, 64, 16))
+    odd = dict(small_scene(n_tris=300, seed=59))
+    odd["bvh"] = tinybvh.add_degenerate_inner_nodes(odd["bvh"].view(tinybvh.NODE)).view(np.uint8).reshape(-1).copy()
+    cases.append((odd, (0.0, 6.0, 1.5), 96, 64, 16))
+    big = dict(small_scene(n_tris=800, seed=12))
+    t = big["triangles"].copy().view(np.float32).reshape(-1, 12)
+    t[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]] *= 1000.0
+    big["triangles"] = t.view(np.uint8).reshape(-1)
+    big["bvh"] = tinybvh.build_bvh(big["triangles"].view(tinybvh.TRI), seed=2).view(np.uint8).reshape(-1).copy()
+    cases.append((big, (0.0, 6000.0, 1500.0), 96, 64, 16 | 4))
+    for sc, cam, w, h, reserved in cases:
+        kw = dict(shader="full", max_bounces=5, sample_count=2, accum="f32", rng="philox", stack_depth=64)
+        a = oracle.render(sc, cam, w, h, make_params(traversal="reference", **kw), want_aov=True)
+        p = make_params(traversal="fast", **kw)
+        p._reserved = reserved
+        b = hostemu.render(sc, cam, w, h, p, want_aov=True)
+        assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), len(sc["triangles"]) // 48
+        assert a["counters"].rays == b["rays"]
+    # scenes the device builder declines (the product then falls back to the host builder)
+    p = make_params(traversal="fast")
+    p._reserved = 16
+    with pytest.raises(RuntimeError, match="too large for 15-bit"):
+        hostemu.render(big, (0.0, 6000.0, 1500.0), 32, 32, p)
+    sc = small_scene(n_tris=8, seed=1)
+    nodes = sc["bvh"].view(tinybvh.NODE).copy()
+    nodes[1]["left"] = 0     # cycle through the root
+    sc["bvh"] = nodes.view(np.uint8).reshape(-1)
+    with pytest.raises(RuntimeError, match="not a plain tree"):
+        hostemu.render(sc, (0.0, 6.0, 1.5), 32, 32, p)
+
+
 def test_brute_force_with_spheres(oracle, hostemu):
     sc = small_scene(n_tris=30, seed=4)
     kw = dict(shader="full", traversal="brute_force", max_bounces=4, sample_count=2)

@@ -2,6 +2,7 @@
 // this library: every render call launches CUDA kernels or fails with an error.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +12,7 @@
 
 #include "../../include/vcrt.h"
 #include "vcrt_ctx.h"
+#include "vcrt_devbuild.h"
 #include "vcrt_host_setup.h"
 #include "vcrt_launch.h"
 #include "vcrt_repack.h"
@@ -97,6 +99,12 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         if (m != c->fast_nodes) { c->fast_nodes = m; c->fast_dirty = true; }
         return VCRT_OK;
     }
+    if (k == "fast_build") {
+        const int m = v == "auto" ? 0 : v == "host" ? 1 : v == "device" ? 2 : -1;
+        if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: fast_build must be 'auto', 'host' or 'device'");
+        if (m != c->fast_build) { c->fast_build = m; c->fast_dirty = true; }
+        return VCRT_OK;
+    }
     if (k == "dispatch_traversal") {
         const int m = v == "auto" ? 0 : v == "reference" ? 1 : v == "fast" ? 2 : -1;
         if (m < 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: dispatch_traversal must be 'auto', 'reference' or 'fast'");
@@ -135,7 +143,7 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
     return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: unknown option '" + k + "'");
 }
 
-static int prepare_fast(vcrt_ctx* c);
+static int prepare_fast(vcrt_ctx* c, bool need_binary = false);
 
 int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
     if (!c || !key || !value || capacity == 0) return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: NULL argument");
@@ -147,6 +155,11 @@ int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
         if (k == "fast_nodes") v = !ok ? "none" : c->wide ? "q15x4" : c->quantized ? "q15" : "f32";
         else if (k == "fast_node_count") v = std::to_string(ok ? (c->wide ? c->nf4nodes : c->nfnodes) : 0u);
         else v = std::to_string(ok ? c->fast_depth : 0u);
+    } else if (k == "fast_build" || k == "fast_build_ms") {
+        CU(c, cudaSetDevice(c->device), "set device");
+        const bool ok = prepare_fast(c) == VCRT_OK;
+        if (k == "fast_build") v = !ok ? "none" : c->built_on_device ? "device" : "host";
+        else { char b[32]; snprintf(b, sizeof b, "%.3f", c->fast_build_ms); v = b; }
     } else if (k == "wf_batch_paths") v = std::to_string(c->wf_batch);
     else if (k == "dispatch_kernel") v = c->dispatch_fast ? "fast" : "reference";
     else if (k == "device") v = std::to_string(c->device);
@@ -208,15 +221,8 @@ static int set_buffer_common(vcrt_ctx* c, int binding, const void* src, size_t b
     if (rc) return rc;
     if (bytes) CU(c, cudaMemcpyAsync(c->ssbo[binding].ptr, src, bytes, kind, c->stream), "copy storage buffer");
     if (binding == VCRT_BINDING_TRIANGLES || binding == VCRT_BINDING_BVH) {
-        std::vector<uint8_t>& shadow = binding == VCRT_BINDING_TRIANGLES ? c->host_tris : c->host_bvh;
-        shadow.resize(bytes);
-        if (bytes) {
-            if (kind == cudaMemcpyHostToDevice) std::memcpy(shadow.data(), src, bytes);
-            else {
-                CU(c, cudaMemcpyAsync(shadow.data(), src, bytes, cudaMemcpyDeviceToHost, c->stream), "read back storage buffer");
-                CU(c, cudaStreamSynchronize(c->stream), "synchronize");
-            }
-        }
+        // the host-side record build reads these two buffers back from the device if and when it runs (fetch_host_copies)
+        (binding == VCRT_BINDING_TRIANGLES ? c->host_tris_valid : c->host_bvh_valid) = false;
         c->fast_dirty = true;
     }
     if (kind == cudaMemcpyHostToDevice) CU(c, cudaStreamSynchronize(c->stream), "synchronize");  // host pointer is borrowed for the call only
@@ -269,20 +275,63 @@ static void harvest_events(vcrt_ctx* c) {
     c->trace_timer.harvest(&c->trace_ms, &c->trace_launches);
 }
 
-static int prepare_fast(vcrt_ctx* c) {
-    if (c->fast_dirty) {
+static int fetch_host_copies(vcrt_ctx* c) {
+    for (int b : {VCRT_BINDING_TRIANGLES, VCRT_BINDING_BVH}) {
+        bool& valid = b == VCRT_BINDING_TRIANGLES ? c->host_tris_valid : c->host_bvh_valid;
+        if (valid) continue;
+        std::vector<uint8_t>& shadow = b == VCRT_BINDING_TRIANGLES ? c->host_tris : c->host_bvh;
+        shadow.resize(c->ssbo[b].bytes);
+        if (c->ssbo[b].bytes) CU(c, cudaMemcpyAsync(shadow.data(), c->ssbo[b].ptr, c->ssbo[b].bytes, cudaMemcpyDeviceToHost, c->stream), "read back storage buffer");
+        CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+        valid = true;
+    }
+    return VCRT_OK;
+}
+
+// Traversal records of the fast path.  Built on the device whenever the default tree is asked for (a rebuilt topology walked as
+// 4-wide quantised nodes) and the scene allows it; otherwise -- other node formats, the bound topology, the megakernel (which
+// walks binary nodes), scenes the device builder declines -- by the host builder (vcrt_repack.cpp), which also words the errors.
+static int prepare_fast(vcrt_ctx* c, bool need_binary) {
+    if (c->fast_dirty || (need_binary && c->fast_ok && !c->have_binary)) {
         // The context counts as prepared only once every record is on the device: any early return below leaves it dirty, so the
         // next render retries (or fails again) instead of launching with missing or stale node / triangle buffers.
+        const auto t0 = std::chrono::steady_clock::now();
         c->fast_ok = false;
-        FastBvh fb;
+        c->fast_dirty = true;
         c->fast_err.clear();
+        const uint32_t nbvh = (uint32_t)(c->ssbo[VCRT_BINDING_BVH].bytes / sizeof(vcrt_bvh_node)), ntris = (uint32_t)(c->ssbo[VCRT_BINDING_TRIANGLES].bytes / sizeof(vcrt_triangle));
+        const bool device_tree = c->fast_sah && (c->fast_nodes == 0 || c->fast_nodes == 3) && !need_binary;
+        if (c->fast_build == 2 && !device_tree) return fail(c, VCRT_ERR_INVALID, "fast_build=device builds the rebuilt 4-wide quantised tree only (fast_bvh=sah, fast_nodes=auto|q15x4, no megakernel)");
+        if (c->fast_build == 2 || (c->fast_build == 0 && device_tree && c->auto_device)) {
+            devbuild::Alloc alloc;
+            alloc.ftris = [c](size_t bytes) { return ensure(c, c->ftris, bytes, "allocate repacked triangles") ? nullptr : c->ftris.ptr; };
+            alloc.q4nodes = [c](size_t bytes) { return ensure(c, c->q4nodes, bytes, "allocate 4-wide nodes") ? nullptr : c->q4nodes.ptr; };
+            devbuild::Result r;
+            std::string why;
+            const int rc = devbuild::run(c->ssbo[VCRT_BINDING_BVH].ptr, nbvh, c->ssbo[VCRT_BINDING_TRIANGLES].ptr, ntris, c->fast_nodes == 3 ? 3.0e38f : 2.5e-4f,
+                                         VCRT_FAST_STACK, c->stream, alloc, r, why);
+            if (rc < 0) return fail(c, VCRT_ERR_CUDA, "failed to build traversal records on the device: " + why);
+            if (rc == 0) {
+                c->quantized = true; c->wide = true; c->have_binary = false; c->built_on_device = true;
+                c->froot4 = r.root4; c->nf4nodes = r.nwide;
+                std::memcpy(c->qorg, r.qorg, sizeof c->qorg); std::memcpy(c->qext, r.qext, sizeof c->qext);
+                c->froot = (int32_t)0x80000000; c->nfnodes = 0;
+                c->fast_depth = r.depth; c->bound_depth = r.bound_depth;
+                c->fast_ok = true; c->fast_dirty = false;
+                c->fast_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                return VCRT_OK;
+            }
+            if (c->fast_build == 2) { c->fast_dirty = false; c->fast_err = why; return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable (fast_build=device): " + why); }
+        }
+        int rc = fetch_host_copies(c);
+        if (rc) return rc;
+        FastBvh fb;
         bool ok = build_fast_bvh((const vcrt_bvh_node*)c->host_bvh.data(), (uint32_t)(c->host_bvh.size() / sizeof(vcrt_bvh_node)),
                                  (const vcrt_triangle*)c->host_tris.data(), (uint32_t)(c->host_tris.size() / sizeof(vcrt_triangle)), fb, c->fast_err);
         if (ok && c->fast_sah) ok = rebuild_fast_bvh_sah(fb, c->fast_err);
         if (ok) ok = check_fast_depth(fb, c->fast_err);   // the tree that will be walked: a deep bound tree is fine once rebuilt
         if (!ok) { c->fast_dirty = false; return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err); }   // a property of the bound tree: no retry
         precompute_triangles(fb);
-        int rc;
         if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris64.size() * 4, "allocate repacked triangles"))) return rc;
         if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
         if (!fb.tris64.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris64.data(), fb.tris64.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
@@ -299,7 +348,7 @@ static int prepare_fast(vcrt_ctx* c) {
             CU(c, cudaMemcpyAsync(c->qnodes.ptr, fb.qnodes.data(), fb.qnodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload quantised nodes");
         }
         CU(c, cudaStreamSynchronize(c->stream), "synchronize");
-        c->quantized = quantized; c->wide = wide;
+        c->quantized = quantized; c->wide = wide; c->have_binary = true; c->built_on_device = false;
         if (wide) { c->froot4 = fb.root4; c->nf4nodes = (uint32_t)(fb.q4nodes.size() / 16); }
         if (quantized) { std::memcpy(c->qorg, fb.qorg, sizeof c->qorg); std::memcpy(c->qext, fb.qext, sizeof c->qext); }
         c->froot = fb.root;
@@ -308,6 +357,7 @@ static int prepare_fast(vcrt_ctx* c) {
         c->bound_depth = fb.bound_depth;
         c->fast_ok = true;
         c->fast_dirty = false;
+        c->fast_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     if (!c->fast_ok) return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err);
     return VCRT_OK;
@@ -331,11 +381,11 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     s.lights = (const vcrt_light*)c->ssbo[VCRT_BINDING_LIGHTS].ptr; s.nlights = (uint32_t)(c->ssbo[VCRT_BINDING_LIGHTS].bytes / sizeof(vcrt_light));
     s.spheres = (const float4*)c->ssbo[VCRT_BINDING_SPHERES].ptr;  s.nspheres = (uint32_t)(c->ssbo[VCRT_BINDING_SPHERES].bytes / sizeof(vcrt_sphere));
     if (p.traversal == VCRT_TRAVERSAL_FAST) {
-        int rc = prepare_fast(c);
+        int rc = prepare_fast(c, (p.flags & VCRT_FLAG_MEGAKERNEL) != 0);   // the megakernel walks the binary nodes
         if (rc) return rc;
-        s.fnodes = (const float4*)c->fnodes.ptr; s.ftris = (const float4*)c->ftris.ptr; s.nfnodes = c->nfnodes; s.froot = c->froot;
+        s.fnodes = c->have_binary ? (const float4*)c->fnodes.ptr : nullptr; s.ftris = (const float4*)c->ftris.ptr; s.nfnodes = c->nfnodes; s.froot = c->froot;
         if (c->quantized) {
-            s.qnodes = (const Words8*)c->qnodes.ptr;
+            s.qnodes = c->have_binary ? (const Words8*)c->qnodes.ptr : nullptr;
             s.qorg = make_float3(c->qorg[0], c->qorg[1], c->qorg[2]);
             s.qext = make_float3(c->qext[0], c->qext[1], c->qext[2]);
         }
@@ -371,10 +421,13 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && a.sample_count == 1u && a.env.max_bounces <= 4u) { a.flags |= VCRT_FLAG_STATIC_KERNEL; one_launch = true; }
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch) {
         // wavefront pipeline: a batch = a range of pixels x all samples of the call; queues sized for what the call needs, at most
-        // wf_batch paths per batch.  Small renders (a 1-spp frame) are cut into up to four batches that run as parallel pipelines on
-        // their own streams, so that the tails of their trace launches overlap (option "wf_streams").
+        // wf_batch paths per batch.  Option "wf_streams" = n cuts the call into n batches that run as parallel pipelines on their
+        // own streams (each with its own queue set), so that the tail of one trace launch overlaps the others' work; "auto" = 1:
+        // measured on C3 (r02_v1), a 1-spp 1080p frame takes 2.19 ms as one pipeline and 2.41 ms as four -- every trace launch of a
+        // small frame lasts as long as its longest ray (~0.2 ms) whatever its size, and four times as many launches cost more
+        // than the overlap returns.
         const uint64_t need = (uint64_t)a.owned_tiles * 1024u * a.sample_count;
-        int sets = c->wf_streams ? c->wf_streams : (need <= (32ull << 20) && need >= (256ull << 10) ? VCRT_MAX_PIPES : 1);
+        int sets = c->wf_streams ? c->wf_streams : 1;
         uint64_t per_set = (need + (uint64_t)sets - 1) / (uint64_t)sets;
         per_set = (per_set + a.sample_count - 1) / a.sample_count * a.sample_count;   // whole pixels
         if (per_set > c->wf_batch) per_set = c->wf_batch;
