@@ -10,9 +10,11 @@ SPHERE = np.dtype([("s", "<f4", 4), ("materialIndex", "<u4"), ("p", "<u4", 3)])
 assert TRI.itemsize == 48 and MAT.itemsize == 32 and NODE.itemsize == 48 and LIGHT.itemsize == 8 and SPHERE.itemsize == 32
 
 
-def build_bvh(tris, seed=0, numbering="reference"):
+def build_bvh(tris, seed=0, numbering="reference", tie_seed=None):
     """Median split on a seeded random axis, one triangle per leaf, nodes numbered like Bvh.h:141-209
-    (children get consecutive indices when their parent is popped; right subtree processed first)."""
+    (children get consecutive indices when their parent is popped; right subtree processed first).
+    tie_seed: triangles with equal sort keys (duplicates) keep a seeded random relative order instead of their index order, so
+    that either copy may end up first in the traversal order."""
     rs = np.random.RandomState(seed)
     n = len(tris)
     lo = np.minimum(np.minimum(tris["v0"], tris["v1"]), tris["v2"]) - np.float32(1e-4)
@@ -22,7 +24,7 @@ def build_bvh(tris, seed=0, numbering="reference"):
     if n == 0:
         return nodes[:0]
     counter = 1
-    stack = [(0, np.arange(n))]
+    stack = [(0, np.arange(n) if tie_seed is None else np.random.RandomState(tie_seed).permutation(n))]
     while stack:
         idx, ids = stack.pop()
         nodes[idx]["min"] = lo[ids].min(axis=0)

@@ -5,14 +5,16 @@ tag=${1:-run}
 out=gpurun_out/$tag
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $out/gpu.txt 2>&1
-python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
+python -m pytest tests -m gpu -q > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1
 python bench.py > $out/bench.json 2> $out/bench.err
+python tools/latency.py > $out/latency.log 2>&1
+python tools/latency.py --bundled >> $out/latency.log 2>&1
 for lib in ${AB_LIBS:-lib}; do
   echo "== $lib C3" >> $out/ab.log
-  VCRT_LIB=$PWD/vulkan_compute_ray_tracing_b200/$lib/libvcrt.so timeout 300 python tools/sweep.py --spp 16 --trace 2>&1 | grep Mrays >> $out/ab.log
+  VCRT_LIB=$PWD/vulkan_compute_ray_tracing_b200/$lib/libvcrt.so timeout 300 python tools/sweep.py --spp 16 --trace $AB_ARGS 2>&1 | grep Mrays >> $out/ab.log
   echo "== $lib C4" >> $out/ab.log
-  VCRT_LIB=$PWD/vulkan_compute_ray_tracing_b200/$lib/libvcrt.so timeout 400 python tools/sweep.py --triangles 10000000 --spp 8 --trace 2>&1 | grep Mrays >> $out/ab.log
+  VCRT_LIB=$PWD/vulkan_compute_ray_tracing_b200/$lib/libvcrt.so timeout 400 python tools/sweep.py --triangles 10000000 --spp 8 --trace $AB_ARGS 2>&1 | grep Mrays >> $out/ab.log
 done
 if [ "$2" != "quick" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-c4 > $out/bench_under_ncu.log 2>&1

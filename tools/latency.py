@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""1-spp frame latency (the reference's own unit, ms/frame: main.cpp:397-413) of the progressive frame loop -- UBO in, one sample
+on top of the accumulation, resolve, rgba8 frame back to pinned host memory -- per kernel family.  DEV TOOL.
+usage: python tools/latency.py [--triangles N | --bundled] [--frames 64]"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vulkan_compute_ray_tracing_b200 as vcrt
+from vulkan_compute_ray_tracing_b200 import scenegen, _native
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--triangles", type=int, default=1000000)
+ap.add_argument("--bundled", action="store_true")
+ap.add_argument("--frames", type=int, default=64)
+ap.add_argument("--bounces", type=int, default=8)
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1080)
+a = ap.parse_args()
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+scene = vcrt.load_scene(os.path.join(root, "tests", "golden", "doge_scene.vcrt")) if a.bundled else scenegen.generate_box_scene(a.triangles, seed=1234)
+w, h = a.width, a.height
+ubo = vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), vcrt.pack_ubo(vcrt.CAMERA_START, 0, scene))
+m = vcrt.ComputeMaterial("ray-trace-compute.spv")
+m.addUniformBufferBundle(ubo)
+m.addStorageImage(vcrt.Image(w, h)); m.addStorageImage(vcrt.Image(w, h))
+for n in ("triangles", "materials", "bvh", "lights", "spheres"):
+    m.addStorageBufferBundle(vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), scene[n]))
+model = vcrt.ComputeModel(m)
+L = _native.lib()
+out = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
+for name, flags, opts in (("wavefront", 0, {}), ("wavefront no trace timing", 0, {"trace_timing": "off"}), ("wavefront 2 pipelines", 0, {"wf_streams": "2"}),
+                          ("megakernel", 16, {}), ("one thread per pixel", 8, {})):
+    for k, v in {"trace_timing": "on", "wf_streams": "auto", **opts}.items():
+        m.setOption(k, v)
+    p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=a.bounces, sample_count=1, flags=flags)
+
+    def frame(k):
+        ubo.buffers[0].write(vcrt.pack_ubo(vcrt.CAMERA_START, k, scene))
+        p.sample_begin = k
+        model.renderCommand(None, 0, p)
+        m.resolve(k + 1, 0.0)
+        m._check(L.vcrt_read_target_rgba8(m._ctx, out.ctypes.data, out.nbytes))
+    m.clearAccum()
+    for k in range(4):
+        frame(k)
+    m.resetCounters()
+    t0 = time.perf_counter()
+    for k in range(4, 4 + a.frames):
+        frame(k)
+    dt = time.perf_counter() - t0
+    c = m.counters()
+    print("%-28s %.3f ms/frame  %.0f Mrays/s  (%d launches/frame, kernels %.3f ms/frame)" % (name, 1e3 * dt / a.frames, c.rays / dt / 1e6, c.launches / a.frames, c.kernel_ms / a.frames), flush=True)

@@ -37,6 +37,17 @@ __global__ void fill_kernel(Rec* rec, size_t n, unsigned mask) {
     }
 }
 
+// the same chase over 64-byte records read as two adjacent 256-bit loads (the trace kernel's node / triangle fetch): table of n64 records
+__global__ void __launch_bounds__(128) chase64_kernel(const Rec* __restrict__ rec, unsigned mask64, int steps, unsigned* out) {
+    unsigned ia = mix32(blockIdx.x * blockDim.x + threadIdx.x) & mask64, acc = 0u;
+    for (int s = 0; s < steps; ++s) {
+        const Rec a = ldg256(rec + 2 * (size_t)ia), b = ldg256(rec + 2 * (size_t)ia + 1);
+        acc ^= a.a[0] ^ a.a[1] ^ a.a[2] ^ a.a[3] ^ a.a[5] ^ a.a[6] ^ a.a[7] ^ b.a[0] ^ b.a[3] ^ b.a[7];
+        ia = (a.a[4] ^ (b.a[4] >> 1)) & mask64;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <int CHAINS>
 __global__ void __launch_bounds__(128) chase_kernel(const Rec* __restrict__ rec, unsigned mask, int steps, unsigned* out) {
     unsigned ia = mix32(blockIdx.x * blockDim.x + threadIdx.x) & mask, ib = mix32(ia + 977u) & mask, acc = 0u;
@@ -89,6 +100,37 @@ extern "C" int vcrt_probe_gather(int device, int records_log2, int steps, int ch
     cudaFree(d); cudaFree(out);
     if (err != cudaSuccess) return -4;
     *g_per_s = (double)blocks * threads * steps * chains / (best * 1e-3) / 1e9;
+    return 0;
+}
+
+// 64-byte records (two adjacent sectors per gather): returns G records/s; bytes/s = 64 x that
+extern "C" int vcrt_probe_gather64(int device, int records_log2, int steps, int reps, double* g_per_s) {
+    if (!g_per_s || records_log2 < 4 || records_log2 > 27 || steps < 1) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t n = (size_t)1 << records_log2;
+    const int blocks = sms * 10 * 6, threads = 128;
+    Rec* d = nullptr; unsigned* out = nullptr;
+    if (cudaMalloc(&d, n * 2 * sizeof(Rec)) != cudaSuccess || cudaMalloc(&out, (size_t)blocks * threads * 4) != cudaSuccess) { cudaFree(d); return -3; }
+    fill_kernel<<<sms * 8, 256>>>(d, n * 2, 0xffffffffu);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep <= reps; ++rep) {
+        cudaEventRecord(e0);
+        chase64_kernel<<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d); cudaFree(out);
+    if (err != cudaSuccess) return -4;
+    *g_per_s = (double)blocks * threads * steps / (best * 1e-3) / 1e9;
     return 0;
 }
 
