@@ -556,7 +556,7 @@ def main():
         mat.setOption("fast_build", "device")
         v, ms = timed(True, min(args.steps, 3))
         e2e["with_scene_upload"] = {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms,
-                                    "record_build": mat.getInfo("fast_build"), "record_build_ms": float(mat.getInfo("fast_build_ms")),
+                                    "record_build": mat.getInfo("fast_build"), "record_build_ms": float(mat.getInfo("fast_build_ms")), "record_build_stages": mat.getInfo("fast_build_stages"),
                                     "includes": "upload of the 5 scene buffers from pinned host memory + rebuild of the traversal records on the device, every step"}
         mat.setOption("fast_build", "host")
         v, ms = timed(True, min(args.steps, 2))

@@ -255,8 +255,8 @@ class ComputeMaterial:
     def getInfo(self, key):
         """Read-only facts as text, e.g. getInfo("fast_nodes") -> "q15x4" | "q15" | "f32" | "none"."""
         self._require()
-        buf = C.create_string_buffer(64)
-        self._check(N.lib().vcrt_get_info(self._ctx, key.encode(), buf, 64))
+        buf = C.create_string_buffer(256)
+        self._check(N.lib().vcrt_get_info(self._ctx, key.encode(), buf, 256))
         return buf.value.decode()
 
     def setStream(self, cuda_stream):

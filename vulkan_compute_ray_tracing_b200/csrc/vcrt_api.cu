@@ -155,10 +155,11 @@ int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
         if (k == "fast_nodes") v = !ok ? "none" : c->wide ? "q15x4" : c->quantized ? "q15" : "f32";
         else if (k == "fast_node_count") v = std::to_string(ok ? (c->wide ? c->nf4nodes : c->nfnodes) : 0u);
         else v = std::to_string(ok ? c->fast_depth : 0u);
-    } else if (k == "fast_build" || k == "fast_build_ms") {
+    } else if (k == "fast_build" || k == "fast_build_ms" || k == "fast_build_stages") {
         CU(c, cudaSetDevice(c->device), "set device");
         const bool ok = prepare_fast(c) == VCRT_OK;
         if (k == "fast_build") v = !ok ? "none" : c->built_on_device ? "device" : "host";
+        else if (k == "fast_build_stages") v = ok && c->built_on_device ? c->fast_build_stages : "";
         else { char b[32]; snprintf(b, sizeof b, "%.3f", c->fast_build_ms); v = b; }
     } else if (k == "wf_batch_paths") v = std::to_string(c->wf_batch);
     else if (k == "dispatch_kernel") v = c->dispatch_fast ? "fast" : "reference";
@@ -319,6 +320,10 @@ static int prepare_fast(vcrt_ctx* c, bool need_binary) {
                 c->fast_depth = r.depth; c->bound_depth = r.bound_depth;
                 c->fast_ok = true; c->fast_dirty = false;
                 c->fast_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                char stages[160];
+                snprintf(stages, sizeof stages, "ranks %.2f ms, records+sort %.2f, PLOC %.2f (%u rounds), collapse %.2f (%u levels)", r.ms_ranks, r.ms_sort - r.ms_ranks,
+                         r.ms_ploc - r.ms_sort, r.ploc_rounds, r.ms_total - r.ms_ploc, r.wide_levels);
+                c->fast_build_stages = stages;
                 return VCRT_OK;
             }
             if (c->fast_build == 2) { c->fast_dirty = false; c->fast_err = why; return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable (fast_build=device): " + why); }

@@ -30,6 +30,7 @@ struct vcrt_ctx {
     bool built_on_device = false;         // where the current records came from
     bool have_binary = false;             // binary node records (fnodes / qnodes) exist: the megakernel and the q15 / f32 formats walk those
     double fast_build_ms = 0.0;           // wall time of the last record build
+    std::string fast_build_stages;        // device builds: where that time went
     bool fast_dirty = true;
     uint32_t continue_threshold = 20;   // option "continue_threshold" (33 - min(leaf, shade) leaves the schedule unchanged)
     uint32_t leaf_threshold = 6, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")

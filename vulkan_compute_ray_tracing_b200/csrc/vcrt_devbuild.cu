@@ -1,9 +1,11 @@
 // vcrt_devbuild.cu -- kernels and driver of the on-device record build (algorithm and per-element bodies: vcrt_devbuild.cuh).
 #include <cub/cub.cuh>
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "vcrt_devbuild.h"
 #include "vcrt_devbuild.cuh"
@@ -100,6 +102,17 @@ int run(const void* d_bvh, uint32_t nbvh, const void* d_tris, uint32_t ntris, fl
         std::string& why) {
     why.clear();
     if (nbvh < 3) { why = "fewer than two leaves"; return 1; }
+    {   // scratch comes from the device's stream-ordered pool: keep what it has handed out across builds instead of returning it
+        // to the driver at every synchronise (the default), or each build pays for a few hundred MB of fresh allocations
+        int dev = 0;
+        cudaMemPool_t pool = nullptr;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&t_begin]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     Temp tmp(stream);
     View v;
     v.bvh = (const vcrt_bvh_node*)d_bvh; v.nbvh = nbvh; v.tris = (const vcrt_triangle*)d_tris; v.ntris = ntris;
@@ -119,6 +132,7 @@ int run(const void* d_bvh, uint32_t nbvh, const void* d_tris, uint32_t ntris, fl
     DB_CU(cudaStreamSynchronize(stream));
     if (h_status[ST_ERROR]) { why = "the bound tree is not a plain tree (shared subtree, cycle, leaf with children or depth > 4096): flags " + std::to_string(h_status[ST_ERROR]); return 1; }
     if (nleaves < 2) { why = "fewer than two leaves"; return 1; }
+    out.ms_ranks = since();
     DB_CU(tmp.get(&v.leaf_node, nleaves));
     DB_CU(cudaMemsetAsync(v.leaf_node, 0xff, (size_t)nleaves * 4, stream));
     k_rank<<<blocks_for(nbvh), kBlock, 0, stream>>>(v, nleaves);
@@ -144,6 +158,8 @@ int run(const void* d_bvh, uint32_t nbvh, const void* d_tris, uint32_t ntris, fl
     DB_CU(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)nleaves, 0, 63, stream));
     k_gather<<<blocks_for(nleaves), kBlock, 0, stream>>>(lo_a, hi_a, vals_b, nleaves, lo_b, hi_b);
     // ---- C: PLOC
+    DB_CU(cudaStreamSynchronize(stream));
+    out.ms_sort = since();
     float* nodes;                                  // binary nodes, 16 floats each, in creation order (the root is the last one)
     DB_CU(tmp.get(&nodes, (size_t)(nleaves - 1) * 16));
     float4 *cur_lo = lo_b, *cur_hi = hi_b, *nxt_lo = lo_a, *nxt_hi = hi_a;
@@ -162,6 +178,7 @@ int run(const void* d_bvh, uint32_t nbvh, const void* d_tris, uint32_t ntris, fl
         if (++rounds > 4096) { why = "PLOC did not converge"; return 1; }
     }
     if (node_base != nleaves - 1) { why = "PLOC produced an inconsistent node count"; return 1; }
+    out.ms_ploc = since();
     float4 root_lo, root_hi;
     DB_CU(cudaMemcpyAsync(&root_lo, cur_lo, 16, cudaMemcpyDeviceToHost, stream));
     DB_CU(cudaMemcpyAsync(&root_hi, cur_hi, 16, cudaMemcpyDeviceToHost, stream));
@@ -209,6 +226,7 @@ int run(const void* d_bvh, uint32_t nbvh, const void* d_tris, uint32_t ntris, fl
     out.depth = f2u(root_hi.w); out.bound_depth = h_status[ST_MAXDEPTH];
     out.stack4 = h_status[ST_STACK] + 2;          // + the sentinel slot and the register-held top's spill slot
     out.ploc_rounds = rounds; out.wide_levels = levels;
+    out.ms_total = since();
     if (out.stack4 > max_stack) { why = "the 4-wide tree could ask for " + std::to_string(out.stack4) + " stack entries"; return 1; }
     return 0;
 }

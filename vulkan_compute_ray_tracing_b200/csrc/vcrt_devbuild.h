@@ -22,6 +22,7 @@ struct Result {
     uint32_t bound_depth = 0;     // deepest leaf of the bound bvh[]
     uint32_t stack4 = 0;          // traversal-stack entries the 4-wide tree can ask for
     uint32_t ploc_rounds = 0, wide_levels = 0;
+    double ms_ranks = 0, ms_sort = 0, ms_ploc = 0, ms_total = 0;   // wall time since the start of the build at the end of steps A, B, C, D
 };
 
 // Builds the fast traversal's records from the bound buffers where they lie in device memory.  Returns 0 on success, 1 when

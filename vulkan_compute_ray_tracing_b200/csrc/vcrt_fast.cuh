@@ -26,7 +26,10 @@
 
 namespace vcrt {
 
-#define VCRT_FAST_STACK 64
+#ifndef VCRT_FAST_STACK
+#define VCRT_FAST_STACK 96   /* traversal-stack entries per ray (local memory, touched only as deep as a ray goes).  The 4-wide tree's exact worst case is computed
+                                at build time: 30-40 for the host's SAH trees, 73 for the device's (deeper) PLOC tree of the 10 M-triangle scene */
+#endif
 #define VCRT_FAST_EMPTY ((int32_t)0x80000000)
 
 VCRT_HD float fmin_(float a, float b) { return fminf(a, b); }

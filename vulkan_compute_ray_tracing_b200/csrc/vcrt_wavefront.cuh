@@ -86,10 +86,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
     const SceneView& s = a.scene;
     const uint32_t count = PRIMARY ? b.nitems : w.counts[b.cur];   // PRIMARY: one ray per work item (pixel), shared by its samples
     const float4* __restrict__ rays = w.q[b.cur];
-    if (!PRIMARY && blockIdx.x == 0 && threadIdx.x == 0 && count) {
-        atomicAdd(a.counters + 0, (unsigned long long)count);   // closest-hit queries
-        atomicAdd(a.counters + 4, (unsigned long long)count);   // traversals run
-    }
+    // (queued rays are counted by the shade kernel that consumes this launch's hits: nothing but traversal state lives in this kernel's registers)
     const int leaf_t = (int)a.leaf_threshold, refill_t = (int)a.shade_threshold, cont_t = (int)a.continue_threshold;
 
     uint32_t idx = 0xffffffffu;          // ray in flight (0xffffffff: none)
@@ -223,6 +220,10 @@ __global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __
     const uint32_t count = PRIMARY ? b.npaths : w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
     float4* __restrict__ next = w.q[b.cur ^ 1u];
+    if (!PRIMARY && blockIdx.x == 0 && threadIdx.x == 0 && count) {   // the rays the preceding trace launch walked: one query = one traversal each
+        atomicAdd(a.counters + 0, (unsigned long long)count);
+        atomicAdd(a.counters + 4, (unsigned long long)count);
+    }
     for (uint32_t base = blockIdx.x * 256u; base < count; base += gridDim.x * 256u) {   // base is warp-uniform
         const uint32_t i = base + threadIdx.x;
         bool cont = false, hit = false;
