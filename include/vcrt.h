@@ -66,7 +66,9 @@ enum { VCRT_FLAG_REF_DISPATCH_COVERAGE = 1u, /* only floor(W/32)*32 x floor(H/32
        VCRT_FLAG_WRITE_AOV = 2u,             /* primary-hit AOV (vcrt_aov per pixel) */
        VCRT_FLAG_COUNT_TRAVERSAL = 4u,       /* count node/triangle fetches (slower kernel variant) */
        VCRT_FLAG_STATIC_KERNEL = 8u,         /* fast traversal in the one-thread-per-pixel launch (A/B, debugging) */
-       VCRT_FLAG_MEGAKERNEL = 16u            /* fast traversal in the persistent-warps megakernel instead of the wavefront pipeline (A/B) */ };
+       VCRT_FLAG_MEGAKERNEL = 16u,           /* fast traversal in the persistent-warps megakernel (whole paths per lane, no barrier between bounces) */
+       VCRT_FLAG_WAVEFRONT = 32u             /* fast traversal in the wavefront pipeline whatever the shape of the call */
+       /* none of the three: by the shape of the call -- 1 spp: one launch (depth <= 4: one thread per pixel; deeper: the megakernel), else the wavefront pipeline */ };
 
 typedef struct {
     uint32_t struct_size;    /* = sizeof(vcrt_render_params) */

@@ -66,11 +66,16 @@ def test_dispatch_simple_shader_matches_reference_frame(doge):
 
 
 def trav_kw(trav):
-    """'fast' = wavefront pipeline (default); 'fast_mega' = persistent-warps megakernel; 'fast_static' = one thread per pixel."""
+    """'fast' = wavefront pipeline; 'fast_mega' = persistent-warps megakernel; 'fast_static' = one thread per pixel; 'fast_auto' = what
+    the library picks by the shape of the call."""
     if trav == "fast_static":
         return dict(traversal="fast", flags=8)
     if trav == "fast_mega":
         return dict(traversal="fast", flags=16)
+    if trav == "fast":
+        return dict(traversal="fast", flags=32)
+    if trav == "fast_auto":
+        return dict(traversal="fast")
     return dict(traversal=trav)
 
 
@@ -329,7 +334,7 @@ def test_wavefront_pipelines_and_counters(gpu_doge, oracle, doge):
     a = oracle.render(doge, CAM, 800, 600, make_params(traversal="reference", **kw))
     for streams in ("1", "2", "4", "auto"):
         gpu_doge.material.setOption("wf_streams", streams)
-        b = gpu_doge.render(CAM, traversal="fast", **kw)
+        b = gpu_doge.render(CAM, traversal="fast", flags=32, **kw)
         assert same_bits(a["accumf"], b["accumf"]) and a["counters"].rays == b["counters"].rays, streams
         assert b["counters"].launches > 1
     kw["sample_count"] = 4
@@ -398,15 +403,10 @@ def test_device_record_build(oracle, doge):
         a = oracle.render(sc, c, w, h, make_params(traversal="reference", **kw), want_aov=True)
         g = GpuScene(sc, w, h)
         g.material.setOption("fast_build", "device")
-        for trav in ("fast", "fast_static"):
+        for trav in ("fast", "fast_static", "fast_mega"):
             b = g.render(c, want_aov=True, **trav_kw(trav), **kw)
             assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (len(sc["triangles"]) // 48, trav)
             assert g.material.getInfo("fast_build") == "device"
-        with pytest.raises(vcrt.VcrtError, match="megakernel"):      # the megakernel walks binary nodes, which only the host builder makes
-            g.render(c, **trav_kw("fast_mega"), **kw)
-        g.material.setOption("fast_build", "auto")
-        b = g.render(c, want_aov=True, **trav_kw("fast_mega"), **kw)
-        assert same_bits(a["accumf"], b["accumf"]) and g.material.getInfo("fast_build") == "host"
         g.close()
     # a scene too large for 15-bit bounds: declined by the device builder
     big = dict(small_scene(n_tris=800, seed=12))
@@ -477,8 +477,10 @@ def test_sharding_properties(gpu_doge):
     assert full1["counters"].launches == 1
     parts1 = [gpu_doge.render(CAM, sample_count=1, tile_rank=r, tile_count=3, **one)["accumf"] for r in range(3)]
     assert same_bits(sum(parts1), full1["accumf"])
-    deep1 = gpu_doge.render(CAM, sample_count=1, **dict(kw, max_bounces=8))      # deep paths: the wavefront pipeline
-    assert deep1["counters"].launches > 1
+    deep1 = gpu_doge.render(CAM, sample_count=1, **dict(kw, max_bounces=8))      # deep 1-spp paths: one launch of the megakernel
+    assert deep1["counters"].launches == 1
+    many = gpu_doge.render(CAM, sample_count=2, **dict(kw, max_bounces=8))       # more samples: the wavefront pipeline
+    assert many["counters"].launches > 1
     # resume: continuing on top of a reloaded accumulation equals the uninterrupted render bit-for-bit
     gpu_doge.material.clearAccum()
     gpu_doge.material.writeAccumF32(a)

@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--triangles", type=int, default=1000000)
 ap.add_argument("--bundled", action="store_true")
 ap.add_argument("--frames", type=int, default=64)
-ap.add_argument("--bounces", type=int, default=8)
+ap.add_argument("--bounces", default="8", help="comma-separated depths")
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 a = ap.parse_args()
@@ -32,11 +32,12 @@ for n in ("triangles", "materials", "bvh", "lights", "spheres"):
 model = vcrt.ComputeModel(m)
 L = _native.lib()
 out = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
-for name, flags, opts in (("wavefront", 0, {}), ("wavefront no trace timing", 0, {"trace_timing": "off"}), ("wavefront 2 pipelines", 0, {"wf_streams": "2"}),
-                          ("megakernel", 16, {}), ("one thread per pixel", 8, {})):
+for nb, name, flags, opts in [(int(nb), n_, f_, o_) for nb in a.bounces.split(",") for n_, f_, o_ in (
+        ("wavefront", 0, {}), ("wavefront no trace timing", 0, {"trace_timing": "off"}), ("megakernel", 16, {}), ("one thread per pixel", 8, {}))]:
     for k, v in {"trace_timing": "on", "wf_streams": "auto", **opts}.items():
         m.setOption(k, v)
-    p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=a.bounces, sample_count=1, flags=flags)
+    p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=nb, sample_count=1, flags=flags)
+    name = "depth %d %s" % (nb, name)
 
     def frame(k):
         ubo.buffers[0].write(vcrt.pack_ubo(vcrt.CAMERA_START, k, scene))
@@ -53,4 +54,4 @@ for name, flags, opts in (("wavefront", 0, {}), ("wavefront no trace timing", 0,
         frame(k)
     dt = time.perf_counter() - t0
     c = m.counters()
-    print("%-28s %.3f ms/frame  %.0f Mrays/s  (%d launches/frame, kernels %.3f ms/frame)" % (name, 1e3 * dt / a.frames, c.rays / dt / 1e6, c.launches / a.frames, c.kernel_ms / a.frames), flush=True)
+    print("%-36s %.3f ms/frame  %.0f Mrays/s  (%d launches/frame, kernels %.3f ms/frame)" % (name, 1e3 * dt / a.frames, c.rays / dt / 1e6, c.launches / a.frames, c.kernel_ms / a.frames), flush=True)

@@ -22,7 +22,7 @@ TRAVERSAL = {"reference": 0, "fast": 1, "brute_force": 2}
 RNG = {"pcg_ref": 0, "philox": 1}
 ACCUM = {"rgba8_ref": 0, "f32": 1}
 TRIG = {"libm": 0, "portable": 1}
-FLAG_REF_DISPATCH_COVERAGE, FLAG_WRITE_AOV, FLAG_COUNT_TRAVERSAL, FLAG_STATIC_KERNEL, FLAG_MEGAKERNEL = 1, 2, 4, 8, 16
+FLAG_REF_DISPATCH_COVERAGE, FLAG_WRITE_AOV, FLAG_COUNT_TRAVERSAL, FLAG_STATIC_KERNEL, FLAG_MEGAKERNEL, FLAG_WAVEFRONT = 1, 2, 4, 8, 16, 32
 
 AOV_DTYPE = np.dtype([("triangle", "<i4"), ("material", "<i4"), ("t", "<f4"), ("backFace", "<u4")])
 RECORD_BYTES = {"triangles": 48, "materials": 32, "bvh": 48, "lights": 8, "spheres": 32}

@@ -143,7 +143,7 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
     return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: unknown option '" + k + "'");
 }
 
-static int prepare_fast(vcrt_ctx* c, bool need_binary = false);
+static int prepare_fast(vcrt_ctx* c);
 
 int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
     if (!c || !key || !value || capacity == 0) return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: NULL argument");
@@ -289,11 +289,10 @@ static int fetch_host_copies(vcrt_ctx* c) {
     return VCRT_OK;
 }
 
-// Traversal records of the fast path.  Built on the device whenever the default tree is asked for (a rebuilt topology walked as
-// 4-wide quantised nodes) and the scene allows it; otherwise -- other node formats, the bound topology, the megakernel (which
-// walks binary nodes), scenes the device builder declines -- by the host builder (vcrt_repack.cpp), which also words the errors.
-static int prepare_fast(vcrt_ctx* c, bool need_binary) {
-    if (c->fast_dirty || (need_binary && c->fast_ok && !c->have_binary)) {
+// Traversal records of the fast path: by the host builder (vcrt_repack.cpp: binned SAH, every node format, the precise error
+// messages) or, for the default tree (a rebuilt topology walked as 4-wide quantised nodes), by the device builder (vcrt_devbuild.cu).
+static int prepare_fast(vcrt_ctx* c) {
+    if (c->fast_dirty) {
         // The context counts as prepared only once every record is on the device: any early return below leaves it dirty, so the
         // next render retries (or fails again) instead of launching with missing or stale node / triangle buffers.
         const auto t0 = std::chrono::steady_clock::now();
@@ -301,8 +300,8 @@ static int prepare_fast(vcrt_ctx* c, bool need_binary) {
         c->fast_dirty = true;
         c->fast_err.clear();
         const uint32_t nbvh = (uint32_t)(c->ssbo[VCRT_BINDING_BVH].bytes / sizeof(vcrt_bvh_node)), ntris = (uint32_t)(c->ssbo[VCRT_BINDING_TRIANGLES].bytes / sizeof(vcrt_triangle));
-        const bool device_tree = c->fast_sah && (c->fast_nodes == 0 || c->fast_nodes == 3) && !need_binary;
-        if (c->fast_build == 2 && !device_tree) return fail(c, VCRT_ERR_INVALID, "fast_build=device builds the rebuilt 4-wide quantised tree only (fast_bvh=sah, fast_nodes=auto|q15x4, no megakernel)");
+        const bool device_tree = c->fast_sah && (c->fast_nodes == 0 || c->fast_nodes == 3);
+        if (c->fast_build == 2 && !device_tree) return fail(c, VCRT_ERR_INVALID, "fast_build=device builds the rebuilt 4-wide quantised tree only (fast_bvh=sah, fast_nodes=auto|q15x4)");
         if (c->fast_build == 2 || (c->fast_build == 0 && device_tree && c->auto_device)) {
             devbuild::Alloc alloc;
             alloc.ftris = [c](size_t bytes) { return ensure(c, c->ftris, bytes, "allocate repacked triangles") ? nullptr : c->ftris.ptr; };
@@ -386,7 +385,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     s.lights = (const vcrt_light*)c->ssbo[VCRT_BINDING_LIGHTS].ptr; s.nlights = (uint32_t)(c->ssbo[VCRT_BINDING_LIGHTS].bytes / sizeof(vcrt_light));
     s.spheres = (const float4*)c->ssbo[VCRT_BINDING_SPHERES].ptr;  s.nspheres = (uint32_t)(c->ssbo[VCRT_BINDING_SPHERES].bytes / sizeof(vcrt_sphere));
     if (p.traversal == VCRT_TRAVERSAL_FAST) {
-        int rc = prepare_fast(c, (p.flags & VCRT_FLAG_MEGAKERNEL) != 0);   // the megakernel walks the binary nodes
+        int rc = prepare_fast(c);
         if (rc) return rc;
         s.fnodes = c->have_binary ? (const float4*)c->fnodes.ptr : nullptr; s.ftris = (const float4*)c->ftris.ptr; s.nfnodes = c->nfnodes; s.froot = c->froot;
         if (c->quantized) {
@@ -422,8 +421,14 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     // A 1-spp frame of a shallow shader (the reference's own frame: NUM_BOUNCES 2 or 4) is one launch of the one-thread-per-pixel
     // kernel instead of three launches per bounce of the wavefront pipeline: 0.09 instead of 0.59 ms at 800x600 on the bundled
     // scene, identical results (r01 A/B; with more samples or deeper paths the wavefront pipeline wins at every size).
+    // A deeper 1-spp frame goes to the megakernel: every trace launch of the wavefront pipeline lasts as long as its slowest ray
+    // (~0.27 ms per bounce on C3 whatever the ray count), and eight such tails in a row cost more than the megakernel's lower lane
+    // utilisation: 1.82 vs 2.09 ms per 1080p frame on C3, 0.84 vs 1.10 ms on the bundled scene (profiles/r02_v6_latency_*.log).
     bool one_launch = (p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL)) != 0;
-    if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && a.sample_count == 1u && a.env.max_bounces <= 4u) { a.flags |= VCRT_FLAG_STATIC_KERNEL; one_launch = true; }
+    if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && !(p.flags & VCRT_FLAG_WAVEFRONT) && a.sample_count == 1u) {
+        a.flags |= a.env.max_bounces <= 4u ? VCRT_FLAG_STATIC_KERNEL : VCRT_FLAG_MEGAKERNEL;
+        one_launch = true;
+    }
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch) {
         // wavefront pipeline: a batch = a range of pixels x all samples of the call; queues sized for what the call needs, at most
         // wf_batch paths per batch.  Option "wf_streams" = n cuts the call into n batches that run as parallel pipelines on their

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
     const uint32_t total_items = a.owned_tiles * 1024u;
     const bool f32 = a.accum_mode == VCRT_ACCUM_F32;
     const SceneView& s = a.scene;
-    const bool qn = s.qnodes != nullptr;   // uniform: quantised 32-byte nodes or 64-byte float nodes
+    const bool wide = s.q4nodes != nullptr;   // uniform: 4-wide quantised nodes (the default records) ...
+    const bool qn = s.qnodes != nullptr;      // ... else binary quantised 32-byte nodes, else 64-byte float nodes
 
     // ---- lane state
     bool has_pixel = false, done = false;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
                     bounce = 0;
                     rng_saved = (600u * x + y) * (a.sample_begin + k + 1u);   // random.glsl:19 (unused by Philox)
                 }
-                if (qn) trav_begin<1>(t, s, cur); else trav_begin<0>(t, s, cur);
+                if (wide) trav_begin<2>(t, s, cur); else if (qn) trav_begin<1>(t, s, cur); else trav_begin<0>(t, s, cur);
                 st.rays++;
                 if (bounce == 0) st.prim++;
             }
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
         for (;;) {
             if (t.node >= 0) {
                 if (COUNT) st.nodes++;
-                if (qn) trav_inner_step<1>(t, s, stack); else trav_inner_step<0>(t, s, stack);
+                if (wide) trav_inner_step4(t, s, stack); else if (qn) trav_inner_step<1>(t, s, stack); else trav_inner_step<0>(t, s, stack);
             }
             if (t.node < 0 && t.node != VCRT_FAST_EMPTY && pending == VCRT_FAST_EMPTY) {   // postpone one leaf, keep going
                 pending = t.node;
