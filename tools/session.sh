@@ -1,5 +1,3 @@
-out=gpurun_out/r02_v6; mkdir -p $out
-python tools/latency.py --bounces 1,2,3,4,8 > $out/latency_c3.log 2>&1
-python tools/latency.py --bundled --bounces 1,2,4,8 > $out/latency_bundled.log 2>&1
-python -m pytest tests -m gpu -q -k "device_record or glass_metal_deep or edge_cases or primary_hits or portable_trig" > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
+out=gpurun_out/r02_v9; mkdir -p $out
+python bench.py --config c4 --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_c4_n1.json 2> $out/bench_c4_n1.err
 ls -la $out
