@@ -260,9 +260,9 @@ class Probe:
         rc = self.lib.vcrt_probe_gather(self.device, records_log2, steps, chains, reps, ctypes.byref(out))
         return out.value if rc == 0 else None
 
-    def gather64(self, records_log2, steps=64, reps=3):
+    def gather64(self, records_log2, steps=64, chains=1, reps=3):
         out = ctypes.c_double()
-        rc = self.lib.vcrt_probe_gather64(self.device, records_log2, steps, reps, ctypes.byref(out))
+        rc = self.lib.vcrt_probe_gather64(self.device, records_log2, steps, chains, reps, ctypes.byref(out))
         return out.value if rc == 0 else None
 
     def stream(self, nbytes, passes=8, reps=3):
@@ -548,8 +548,42 @@ def main():
                 return 1e3 * dt / nfr, mat.counters().rays / dt / 1e6
             nfr = 64
             ms1, v1 = frame_loop(nfr)
-            e2e["frame_1spp"] = {"ms_per_frame": ms1, "value": v1, "unit": "Mrays/s", "frames": nfr,
-                                 "protocol": "progressive frame loop, one sample per frame, rgba8 frame read back every frame"}
+
+            # The same loop as the reference runs it: MAX_FRAMES_IN_FLIGHT = 2 frames going at once (main.cpp:68; fences :298-316,
+            # :325, :394) -- vcrt_frames_begin / vcrt_frame_submit / vcrt_frame_wait.  drawFrame waits for the fence of the slot it
+            # reuses, writes the UBO, submits and moves on; every frame's rgba8 image still lands in (page-locked) host memory.
+            def frame_loop_in_flight(nfl, nfr):
+                bufs = [vcrt.PinnedFrame(w, h) for _ in range(nfl)]
+                mat.clearAccum()
+                mat.framesBegin(nfl)
+
+                def submit(k):
+                    ubo.buffers[0].write(vcrt.pack_ubo(CAM, k, scene))
+                    one.sample_begin = k
+                    mat.frameSubmit(one, total_samples=k + 1, gamma=0.0, out=bufs[k % nfl])
+                for k in range(8):
+                    submit(k)
+                mat.synchronize()
+                c0 = mat.counters().rays
+                t0 = time.perf_counter()
+                for k in range(8, 8 + nfr):
+                    submit(k)
+                for s_ in range(nfl):
+                    mat.frameWait(s_)
+                dt = time.perf_counter() - t0
+                r_ = mat.counters().rays - c0
+                mat.framesEnd()
+                for b_ in bufs:
+                    b_.free()
+                return 1e3 * dt / nfr, r_ / dt / 1e6
+            mat.resetCounters()
+            ms2, v2 = frame_loop_in_flight(2, nfr)
+            ms4, v4 = frame_loop_in_flight(4, nfr)
+            e2e["frame_1spp"] = {"ms_per_frame": ms2, "value": v2, "unit": "Mrays/s", "frames": nfr, "frames_in_flight": 2,
+                                 "protocol": "progressive frame loop with the reference's MAX_FRAMES_IN_FLIGHT = 2 (main.cpp:68): per frame UBO write, one sample rendered, folded into "
+                                             "the accumulation in frame order, resolved, rgba8 frame read back into page-locked host memory; frames bit-identical to the synchronous loop",
+                                 "synchronous": {"ms_per_frame": ms1, "value": v1, "what": "one frame at a time: render, resolve, blocking read-back (the latency of a single frame)"},
+                                 "frames_in_flight_4": {"ms_per_frame": ms4, "value": v4}}
         # a scene change every step: the records are rebuilt on the device (fast_build=device: CUDA kernels over the uploaded buffers);
         # `host_build` = the same with the host builder (binned SAH on the CPU cores + upload of its records)
         mat.setOption("fast_build", "device")
@@ -655,7 +689,10 @@ def main():
             pr4 = dict(probes)
             pr = Probe(local_rank)
             dram_gather = pr.gather(26, steps=32)        # 2 GB table of 32-byte records: DRAM-resident
-            dram_gather64 = pr.gather64(25, steps=32)    # 2 GB table of 64-byte records (two adjacent sectors per gather, the kernel's record size)
+            # 2 GB table of 64-byte records (two adjacent sectors per gather, the kernel's record size); 1, 2 and 4 independent chains per
+            # lane -- the ceiling is the rate HBM sustains once enough random reads are in flight, i.e. the largest of the three
+            dram_gather64_by_chains = {ch: pr.gather64(25, steps=32 // ch, chains=ch) for ch in (1, 2, 4)}
+            dram_gather64 = max([v for v in dram_gather64_by_chains.values() if v] or [0.0]) or None
             flush4 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
             def step4():
@@ -678,6 +715,7 @@ def main():
             # bandwidth), measured by the probe; the kernel's real DRAM bytes per launch come from the committed ncu capture.
             roof4["dram_gather32_peak_gbs"] = dram_gather * 32.0 if dram_gather else None
             roof4["dram_gather64_peak_gbs"] = dram_gather64 * 64.0 if dram_gather64 else None
+            roof4["dram_gather64_gbs_by_chains_per_lane"] = {str(k): (v * 64.0 if v else None) for k, v in dram_gather64_by_chains.items()}
             if roof4.get("hbm") and dram_gather64:
                 roof4["hbm"]["random64_peak"] = dram_gather64 * 64.0
                 roof4["hbm"]["frac_of_random64_peak"] = roof4["hbm"]["achieved"] / (dram_gather64 * 64.0)
@@ -685,7 +723,7 @@ def main():
                 roof4["l2_gather"] = {k: roof4[k] for k in ("achieved", "peak", "frac")}
                 roof4["achieved"], roof4["peak"], roof4["frac"] = roof4["hbm"]["achieved"], dram_gather64 * 64.0, roof4["hbm"]["frac_of_random64_peak"]
                 roof4["what"] = ("DRAM bytes per trace launch (ncu dram__bytes_read+write, committed capture) per second of kernel time (live CUDA events), against the rate of "
-                                 "dependent random 64-byte reads from a 2 GB DRAM-resident table measured by the in-process probe")
+                                 "dependent random 64-byte reads from a 2 GB DRAM-resident table measured by the in-process probe (best of 1, 2 and 4 independent chains per lane)")
             line["c4"] = {"workload": "synthetic %d-triangle lit box (seed %d), 1920x1080, 8 spp, depth 8, one GPU" % (len(sc4["triangles"]) // 48, args.scene_seed),
                           "fast_nodes": mat4.getInfo("fast_nodes"), "record_bytes": int(mat4.getInfo("fast_node_count")) * 64 + (len(sc4["triangles"]) // 48) * 64,
                           "value": c4.rays / 3 / (ms4 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms4, "roofline": roof4, "scene_build_s": gen4}

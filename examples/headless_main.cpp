@@ -111,8 +111,18 @@ int main(int argc, char** argv) {
         VkCommandBuffer cmd = nullptr;
         uint32_t currentSample = 0;
         const float camera[3] = {1.8f, 8.6f, 1.1f};   // main.cpp:37
+        // main.cpp:68, :298-316: two frames in flight, each slot behind a fence; what the reference presents to the swapchain lands
+        // in the slot's page-locked buffer here
+        const int MAX_FRAMES_IN_FLIGHT = 2;
+        void* presented[MAX_FRAMES_IN_FLIGHT] = {nullptr, nullptr};
+        const size_t frameBytes = (size_t)W * H * 4;
+        for (auto& p : presented)
+            if (vcrt_alloc_host(frameBytes, &p) != VCRT_OK) throw std::runtime_error(vcrt_last_error(nullptr));
+        computeMaterial->framesBegin(MAX_FRAMES_IN_FLIGHT);
+        size_t currentFrame = 0;
         auto t0 = std::chrono::steady_clock::now();
         for (int frame = 0; frame < frames; ++frame) {
+            computeMaterial->frameWait((uint32_t)currentFrame);   // vkWaitForFences(inFlightFences[currentFrame]), main.cpp:325
             // updateScene, main.cpp:166-183
             UniformBufferObject ubo = {{camera[0], camera[1], camera[2]}, 0.0f, currentSample, (uint32_t)rtScene->triangles.size(), (uint32_t)rtScene->lights.size(), (uint32_t)rtScene->spheres.size()};
             auto& buffer = computeModel->getMaterial()->getUniformBufferBundles()[0].data->buffers[0];
@@ -120,10 +130,15 @@ int main(int argc, char** argv) {
             buffer->unmap();
             currentSample++;
             // main.cpp:228 (ceil-div instead of the reference's floor so the bottom rows are rendered too)
-            computeModel->computeCommand(cmd, 0, (W + 31) / 32, (H + 31) / 32, 1);
+            computeModel->frameCommand(cmd, 0, (W + 31) / 32, (H + 31) / 32, 1, presented[currentFrame], frameBytes);
+            currentFrame = (currentFrame + 1) % MAX_FRAMES_IN_FLIGHT;   // main.cpp:394
         }
-        std::vector<uint8_t> px = targetTexture->read();
+        computeMaterial->framesEnd();   // vkDeviceWaitIdle, main.cpp:419
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::vector<uint8_t> px = targetTexture->read();
+        if (frames > 0 && std::memcmp(px.data(), presented[(frames - 1) % MAX_FRAMES_IN_FLIGHT], frameBytes) != 0)
+            throw std::runtime_error("failed to present: the last presented frame differs from the target image");
+        for (auto& p : presented) vcrt_free_host(p);
         printf("%f ms/frame\n", ms / frames);   // main.cpp:409
         std::ofstream out(argv[2], std::ios::binary);
         out << "P6\n" << W << " " << H << "\n255\n";

@@ -200,6 +200,35 @@ int vcrt_get_counters(vcrt_ctx* ctx, vcrt_counters* out);           /* synchroni
 int vcrt_reset_counters(vcrt_ctx* ctx);
 
 /* ------------------------------------------------------------------------------------------
+ * Frames in flight.  The reference's frame loop keeps MAX_FRAMES_IN_FLIGHT = 2 frames going (main.cpp:68; fences and semaphores
+ * :298-316; drawFrame waits for the fence of the slot it is about to reuse, :325, submits, :367-380, and moves on, :394), so the
+ * "ms/frame" it prints (:397-413) is the rate of a pipelined loop.  The same here: between vcrt_frames_begin and vcrt_frames_end,
+ * vcrt_frame_submit renders ONE sample per pixel on the slot's own stream -- the render kernels of consecutive frames overlap, the
+ * long rays that end one frame run beside the bulk of the next --, folds it into the accumulation IN FRAME ORDER (an event chains the
+ * folds), resolves, and copies the rgba8 frame into `host_dst` (pinned memory: vcrt_alloc_host) while later frames render.  Frames
+ * are bit-identical to the synchronous sequence vcrt_set_ubo / vcrt_render / vcrt_resolve / vcrt_read_target_rgba8.
+ *   params       as for vcrt_render, sample_count 0 or 1; VCRT_ACCUM_RGBA8_REF: the running mean through the rgba8 pair;
+ *                VCRT_ACCUM_F32: the f32 sum, which restarts when params->sample_begin == 0 (as the running mean does: its weight
+ *                of the history is 0 at sample 0, ray-trace-compute.comp:375-379) and is resolved with 1/total_samples
+ *                (0 = sample_begin + 1) and `gamma` as by vcrt_resolve
+ *   host_dst     W*H*4 bytes or NULL (no read-back); valid after vcrt_frame_wait(slot) -- the vkWaitForFences of that slot
+ * While frames are in flight the other calls that touch the context's images or buffers fail with VCRT_ERR_STATE; vcrt_set_ubo,
+ * vcrt_set_option (thresholds), vcrt_get_info and vcrt_last_error are fine.  After vcrt_frames_end the target, the accumulation and
+ * the counters are those of the last frame, as if the frames had been rendered synchronously.
+ * ---------------------------------------------------------------------------------------- */
+#define VCRT_MAX_FRAMES_IN_FLIGHT 4
+int vcrt_frames_begin(vcrt_ctx* ctx, uint32_t frames_in_flight /* 1..4; the reference: 2 */);
+int vcrt_frame_submit(vcrt_ctx* ctx, const vcrt_render_params* params, uint32_t total_samples, float gamma, void* host_dst, size_t bytes, uint32_t* slot);
+/* ComputeModel::computeCommand (vcrt_dispatch: ubo.currentSample, reference RNG, rgba8 running mean, x*32 by y*32 pixels) as a frame in flight */
+int vcrt_frame_dispatch(vcrt_ctx* ctx, uint32_t groups_x, uint32_t groups_y, uint32_t groups_z, void* host_dst, size_t bytes, uint32_t* slot);
+int vcrt_frame_wait(vcrt_ctx* ctx, uint32_t slot);
+int vcrt_frames_end(vcrt_ctx* ctx);
+/* Page-locked host memory for read-backs that overlap rendering (the reference's staging buffers are host-visible VMA
+ * allocations, Buffer.h:42-60).  Any host memory works with every call; only pinned memory keeps vcrt_frame_submit asynchronous. */
+int vcrt_alloc_host(size_t bytes, void** out);
+int vcrt_free_host(void* ptr);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU groups (no reference counterpart: one VkDevice and one queue, VulkanApplicationContext.cpp:95-119; the shader's
  * invocations never communicate, so pixels and samples partition freely -- SURVEY.md 8e).  The scene is replicated; one call
  * renders one frame on all GPUs of the group and combines the shares with ONE NCCL collective on the render streams:

@@ -115,7 +115,13 @@ public:
         check(vcrt_set_ubo(m_ctx, &u));
     }
 
+    // Frames in flight (main.cpp:68 MAX_FRAMES_IN_FLIGHT; fences :298-316; vkWaitForFences :325; vkDeviceWaitIdle :419)
+    void framesBegin(uint32_t framesInFlight) { requireInit(); check(vcrt_frames_begin(m_ctx, framesInFlight)); }
+    void frameWait(uint32_t slot) { check(vcrt_frame_wait(m_ctx, slot)); }
+    void framesEnd() { check(vcrt_frames_end(m_ctx)); }
+
     vcrt_ctx* context() { return m_ctx; }
+    void requireInit() const { if (!m_initialized) throw std::runtime_error("failed to use compute material: init() has not run"); }
     void check(int rc) const { if (rc != VCRT_OK) throw std::runtime_error(vcrt_last_error(m_ctx)); }
 
 private:
@@ -143,6 +149,14 @@ public:
     void computeCommand(VkCommandBuffer& commandBuffer, size_t currentFrame, size_t x, size_t y, size_t z) {
         m_material->bind(commandBuffer, currentFrame);
         m_material->check(vcrt_dispatch(m_material->context(), (uint32_t)x, (uint32_t)y, (uint32_t)z));
+    }
+    // computeCommand as a frame in flight (between framesBegin and framesEnd): rendered on the next slot's stream, presented into
+    // `presented` (W*H*4 bytes, ideally from vcrt_alloc_host; nullptr = no read-back); returns the slot whose fence guards it
+    uint32_t frameCommand(VkCommandBuffer& commandBuffer, size_t currentFrame, size_t x, size_t y, size_t z, void* presented, size_t bytes) {
+        m_material->bind(commandBuffer, currentFrame);
+        uint32_t slot = 0;
+        m_material->check(vcrt_frame_dispatch(m_material->context(), (uint32_t)x, (uint32_t)y, (uint32_t)z, presented, bytes, &slot));
+        return slot;
     }
     // the same path with run-time parameters (sample loop, depth, RNG / accumulation mode, sharding)
     void renderCommand(VkCommandBuffer& commandBuffer, size_t currentFrame, const vcrt_render_params& params) {

@@ -930,3 +930,95 @@ def test_scripted_frame_loop(oracle, doge):
     with pytest.raises(ValueError):
         loop.run("x")
     g.close()
+
+
+@pytest.mark.parametrize("nslots", [1, 2, 4])
+def test_frames_in_flight_dispatch_bit_identical(doge, nslots):
+    """The reference's pipelined loop (MAX_FRAMES_IN_FLIGHT, main.cpp:68, :325, :394): every presented frame of the pipelined
+    FrameLoop -- camera moves (accumulation restarts) included -- equals the frame the synchronous computeCommand sequence leaves in
+    the target, bit for bit."""
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from gpuharness import GpuScene
+    script = "....w..a.d..."
+    g = GpuScene(doge, 320, 240)
+    sync = vcrt.FrameLoop(g.model, doge, 320, 240, frame_time=0.5)
+    want = []
+    for key in script:
+        sync.drawFrame(key)
+        want.append(g.target.read())
+    g.close()
+    g = GpuScene(doge, 320, 240)
+    got = {}
+    loop = vcrt.FrameLoop(g.model, doge, 320, 240, frame_time=0.5, frames_in_flight=nslots, on_present=lambda i, a: got.__setitem__(i, a.copy()))
+    final = loop.run(script)
+    assert sorted(got) == list(range(len(script)))
+    for i in range(len(script)):
+        assert same_bits(got[i], want[i]), i
+    assert same_bits(final, want[-1]) and same_bits(g.accum.read(), want[-1])
+    # the synchronous interface works again after the loop has finished, and refuses to run while frames are in flight
+    g.material.framesBegin(2)
+    with pytest.raises(vcrt.VcrtError, match="frames are in flight"):
+        g.target.read()
+    with pytest.raises(vcrt.VcrtError, match="frames are in flight"):
+        g.model.computeCommand(None, 0, 10, 8, 1)
+    g.material.framesEnd()
+    assert same_bits(g.target.read(), want[-1])
+    with pytest.raises(vcrt.VcrtError, match="vcrt_frames_begin"):
+        g.model.frameCommand(None, 0, 10, 8, 1)
+    g.close()
+
+
+@pytest.mark.parametrize("family", ["static", "mega", "wavefront", "reference"])
+@pytest.mark.parametrize("accum", ["f32", "rgba8_ref"])
+def test_frames_in_flight_render_params(doge, family, accum):
+    """vcrt_frame_submit with run-time parameters, every kernel family: n progressive 1-spp frames in flight against the same
+    frames through vcrt_render + vcrt_resolve + read-back, bit for bit (f32: resolved frame and the accumulation buffer itself)."""
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from gpuharness import GpuScene
+    w, h, n = 200, 136, 7      # ragged: not a multiple of the 32x32 tiles
+    flags = {"static": vcrt.FLAG_STATIC_KERNEL, "mega": vcrt.FLAG_MEGAKERNEL, "wavefront": vcrt.FLAG_WAVEFRONT, "reference": 0}[family]
+    kw = dict(shader="full", traversal="reference" if family == "reference" else "fast", rng="philox", accum=accum, trig="libm", max_bounces=5,
+              stack_depth=64, sample_count=1, philox_seed=7, flags=flags)
+    g = GpuScene(doge, w, h)
+    want = []
+    g.set_camera(CAM, 0)
+    g.material.clearAccum()
+    for k in range(n):
+        p = vcrt.render_params(**kw, sample_begin=k)
+        g.model.renderCommand(None, 0, p)
+        if accum == "f32":
+            g.material.resolve(k + 1, 2.2)
+        want.append(g.target.read())
+    want_acc = g.material.readAccumF32() if accum == "f32" else g.accum.read()
+    g.close()
+    g = GpuScene(doge, w, h)
+    g.set_camera(CAM, 0)
+    # stale accumulation: sample 0 restarts it (f32 explicitly, rgba8 through the running mean's zero weight)
+    g.model.renderCommand(None, 0, vcrt.render_params(**kw, sample_begin=3))
+    bufs = [vcrt.PinnedFrame(w, h) for _ in range(3)]
+    g.material.framesBegin(3)
+    got, inflight = [], {}
+    for k in range(n):
+        p = vcrt.render_params(**kw, sample_begin=k)
+        buf = bufs[k % 3]
+        if (k % 3) in inflight:
+            g.material.frameWait(k % 3)
+            got.append(buf.array.copy())
+        slot = g.material.frameSubmit(p, total_samples=k + 1, gamma=2.2, out=buf)
+        assert slot == k % 3
+        inflight[slot] = k
+    for k in range(n, n + 3):
+        if len(got) < n:
+            g.material.frameWait(k % 3)
+            got.append(bufs[k % 3].array.copy())
+    g.material.framesEnd()
+    assert len(got) == n
+    for k in range(n):
+        assert same_bits(got[k], want[k]), (family, accum, k)
+    assert same_bits(g.target.read(), want[-1])
+    assert same_bits(g.material.readAccumF32() if accum == "f32" else g.accum.read(), want_acc)
+    c = g.material.counters()
+    assert c.rays > 0 and c.kernel_ms > 0.0
+    for b in bufs:
+        b.free()
+    g.close()

@@ -19,6 +19,7 @@ ap.add_argument("--frames", type=int, default=64)
 ap.add_argument("--bounces", default="8", help="comma-separated depths")
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--in-flight", default="2,3,4", help="comma-separated numbers of frames in flight for the pipelined loop")
 a = ap.parse_args()
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 scene = vcrt.load_scene(os.path.join(root, "tests", "golden", "doge_scene.vcrt")) if a.bundled else scenegen.generate_box_scene(a.triangles, seed=1234)
@@ -55,3 +56,31 @@ for nb, name, flags, opts in [(int(nb), n_, f_, o_) for nb in a.bounces.split(",
     dt = time.perf_counter() - t0
     c = m.counters()
     print("%-36s %.3f ms/frame  %.0f Mrays/s  (%d launches/frame, kernels %.3f ms/frame)" % (name, 1e3 * dt / a.frames, c.rays / dt / 1e6, c.launches / a.frames, c.kernel_ms / a.frames), flush=True)
+
+
+# ---- the pipelined loop (vcrt_frames_begin / vcrt_frame_submit / vcrt_frame_wait: the reference's MAX_FRAMES_IN_FLIGHT, main.cpp:68)
+for nb in [int(x) for x in a.bounces.split(",")]:
+    for name, flags in (("wavefront", 32), ("megakernel", 16), ("one thread per pixel", 8)):
+        for nfl in [int(x) for x in a.in_flight.split(",")]:
+            p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=nb, sample_count=1, flags=flags)
+            bufs = [vcrt.PinnedFrame(w, h) for _ in range(nfl)]
+            m.clearAccum()
+            m.framesBegin(nfl)
+
+            def submit(k):
+                ubo.buffers[0].write(vcrt.pack_ubo(vcrt.CAMERA_START, k, scene))
+                p.sample_begin = k
+                m.frameSubmit(p, total_samples=k + 1, gamma=0.0, out=bufs[k % nfl])   # waits for the slot's fence first
+            for k in range(8):
+                submit(k)
+            m.synchronize()
+            t0 = time.perf_counter()
+            for k in range(8, 8 + a.frames):
+                submit(k)
+            for s_ in range(nfl):
+                m.frameWait(s_)
+            dt = time.perf_counter() - t0
+            m.framesEnd()
+            for b in bufs:
+                b.free()
+            print("depth %d %-22s %d frames in flight  %.3f ms/frame" % (nb, name, nfl, 1e3 * dt / a.frames), flush=True)

@@ -37,13 +37,24 @@ __global__ void fill_kernel(Rec* rec, size_t n, unsigned mask) {
     }
 }
 
-// the same chase over 64-byte records read as two adjacent 256-bit loads (the trace kernel's node / triangle fetch): table of n64 records
+// the same chase over 64-byte records read as two adjacent 256-bit loads (the trace kernel's node / triangle fetch): table of n64 records.
+// CHAINS independent chains per lane: with one chain a lane has one record in flight; the trace kernel has more than that in flight
+// per lane on average (two halves of a node, a postponed triangle, the stack), so the ceiling of a DRAM-resident table is the
+// largest rate over 1, 2 and 4 chains.
+template <int CHAINS>
 __global__ void __launch_bounds__(128) chase64_kernel(const Rec* __restrict__ rec, unsigned mask64, int steps, unsigned* out) {
-    unsigned ia = mix32(blockIdx.x * blockDim.x + threadIdx.x) & mask64, acc = 0u;
+    unsigned ix[CHAINS], acc = 0u;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) ix[c] = mix32((blockIdx.x * blockDim.x + threadIdx.x) * CHAINS + c) & mask64;
     for (int s = 0; s < steps; ++s) {
-        const Rec a = ldg256(rec + 2 * (size_t)ia), b = ldg256(rec + 2 * (size_t)ia + 1);
-        acc ^= a.a[0] ^ a.a[1] ^ a.a[2] ^ a.a[3] ^ a.a[5] ^ a.a[6] ^ a.a[7] ^ b.a[0] ^ b.a[3] ^ b.a[7];
-        ia = (a.a[4] ^ (b.a[4] >> 1)) & mask64;
+        Rec a[CHAINS], b[CHAINS];
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) { a[c] = ldg256(rec + 2 * (size_t)ix[c]); b[c] = ldg256(rec + 2 * (size_t)ix[c] + 1); }
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            acc ^= a[c].a[0] ^ a[c].a[1] ^ a[c].a[2] ^ a[c].a[3] ^ a[c].a[5] ^ a[c].a[6] ^ a[c].a[7] ^ b[c].a[0] ^ b[c].a[3] ^ b[c].a[7];
+            ix[c] = (a[c].a[4] ^ (b[c].a[4] >> 1) ^ (unsigned)c) & mask64;
+        }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
@@ -104,8 +115,8 @@ extern "C" int vcrt_probe_gather(int device, int records_log2, int steps, int ch
 }
 
 // 64-byte records (two adjacent sectors per gather): returns G records/s; bytes/s = 64 x that
-extern "C" int vcrt_probe_gather64(int device, int records_log2, int steps, int reps, double* g_per_s) {
-    if (!g_per_s || records_log2 < 4 || records_log2 > 27 || steps < 1) return -1;
+extern "C" int vcrt_probe_gather64(int device, int records_log2, int steps, int chains, int reps, double* g_per_s) {
+    if (!g_per_s || records_log2 < 4 || records_log2 > 27 || steps < 1 || (chains != 1 && chains != 2 && chains != 4)) return -1;
     if (cudaSetDevice(device) != cudaSuccess) return -2;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -119,7 +130,9 @@ extern "C" int vcrt_probe_gather64(int device, int records_log2, int steps, int 
     float best = 1e30f;
     for (int rep = 0; rep <= reps; ++rep) {
         cudaEventRecord(e0);
-        chase64_kernel<<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
+        if (chains == 4) chase64_kernel<4><<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
+        else if (chains == 2) chase64_kernel<2><<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
+        else chase64_kernel<1><<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0.0f;
@@ -130,7 +143,7 @@ extern "C" int vcrt_probe_gather64(int device, int records_log2, int steps, int 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d); cudaFree(out);
     if (err != cudaSuccess) return -4;
-    *g_per_s = (double)blocks * threads * steps / (best * 1e-3) / 1e9;
+    *g_per_s = (double)blocks * threads * steps * chains / (best * 1e-3) / 1e9;
     return 0;
 }
 

@@ -65,6 +65,13 @@ SIGNATURES = {
     "vcrt_synchronize": (C.c_int, [_P]),
     "vcrt_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "vcrt_reset_counters": (C.c_int, [_P]),
+    "vcrt_frames_begin": (C.c_int, [_P, C.c_uint32]),
+    "vcrt_frame_submit": (C.c_int, [_P, C.POINTER(RenderParams), C.c_uint32, C.c_float, _P, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "vcrt_frame_dispatch": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "vcrt_frame_wait": (C.c_int, [_P, C.c_uint32]),
+    "vcrt_frames_end": (C.c_int, [_P]),
+    "vcrt_alloc_host": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "vcrt_free_host": (C.c_int, [_P]),
     "vcrt_group_unique_id": (C.c_int, [_P]),
     "vcrt_group_create_local": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
     "vcrt_group_create_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),

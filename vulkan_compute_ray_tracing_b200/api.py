@@ -91,6 +91,30 @@ class Image:
         return self._material._read_image(self._slot)
 
 
+class PinnedFrame:
+    """An (H, W, 4) uint8 frame in page-locked host memory (vcrt_alloc_host): the destination of a read-back that overlaps the
+    rendering of later frames (ComputeMaterial.frameSubmit)."""
+
+    def __init__(self, width, height):
+        self._ptr = C.c_void_p()
+        nbytes = int(width) * int(height) * 4
+        if N.lib().vcrt_alloc_host(nbytes, C.byref(self._ptr)) != 0:
+            raise VcrtError(N.lib().vcrt_last_error(None).decode())
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(C.c_uint8)), shape=(int(height), int(width), 4))
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            N.lib().vcrt_free_host(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Descriptor:
     """Descriptor<T> (Material.h:12-17)."""
 
@@ -278,6 +302,33 @@ class ComputeMaterial:
         self._require()
         self._check(N.lib().vcrt_reset_counters(self._ctx))
 
+    # ---- frames in flight (main.cpp:68 MAX_FRAMES_IN_FLIGHT, :298-316 fences, :325 vkWaitForFences, :394): vcrt_frames_* / vcrt_frame_*
+    def framesBegin(self, frames_in_flight=2):
+        self._require()
+        self._check(N.lib().vcrt_frames_begin(self._ctx, int(frames_in_flight)))
+
+    def frameSubmit(self, params, total_samples=0, gamma=0.0, out=None, currentFrame=0):
+        """One 1-spp frame on the next slot: render, fold into the accumulation in frame order, resolve, read back into `out`
+        (a PinnedFrame or a (H, W, 4) uint8 array; None = no read-back).  Returns the slot; `out` is valid after frameWait(slot).
+        The UBO is buffers[currentFrame] of the uniform bundle, as in bind()."""
+        self._require()
+        if params.shader == 0 and self.m_computeShaderPath.split("/")[-1].split(".")[0] == "ray-trace-compute-simple":
+            params.shader = 1
+        self.bind(None, currentFrame)
+        arr = out.array if isinstance(out, PinnedFrame) else out
+        slot = C.c_uint32()
+        self._check(N.lib().vcrt_frame_submit(self._ctx, C.byref(params), int(total_samples), float(gamma), arr.ctypes.data if arr is not None else None,
+                                              arr.nbytes if arr is not None else 0, C.byref(slot)))
+        return slot.value
+
+    def frameWait(self, slot):
+        self._require()
+        self._check(N.lib().vcrt_frame_wait(self._ctx, int(slot)))
+
+    def framesEnd(self):
+        self._require()
+        self._check(N.lib().vcrt_frames_end(self._ctx))
+
     def destroy(self):
         """~Material (Material.cpp:21-29)."""
         if self._ctx is not None:
@@ -308,6 +359,17 @@ class ComputeModel:
         m = self.m_material
         m.bind(commandBuffer, currentFrame)
         m._check(N.lib().vcrt_dispatch(m._ctx, int(x), int(y), int(z)))
+
+    def frameCommand(self, commandBuffer, currentFrame, x, y, z, out=None):
+        """computeCommand as a frame in flight (vcrt_frame_dispatch; between framesBegin and framesEnd): returns the slot whose
+        fence (frameWait) guards `out`, a PinnedFrame or (H, W, 4) uint8 array that receives the presented rgba8 frame."""
+        m = self.m_material
+        m.bind(commandBuffer, currentFrame)
+        arr = out.array if isinstance(out, PinnedFrame) else out
+        slot = C.c_uint32()
+        m._check(N.lib().vcrt_frame_dispatch(m._ctx, int(x), int(y), int(z), arr.ctypes.data if arr is not None else None, arr.nbytes if arr is not None else 0,
+                                             C.byref(slot)))
+        return slot.value
 
     def renderCommand(self, commandBuffer, currentFrame, params):
         """The same path with run-time parameters (vcrt_render): sample loop, depth, RNG/accumulation mode, sharding."""

@@ -39,6 +39,9 @@ static int cuda_fail(vcrt_ctx* c, cudaError_t e, const char* what) {
 }
 #define CU(c, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, (what)); } while (0)
 
+// calls that touch the context's images, buffers or render stream are not allowed between vcrt_frames_begin and vcrt_frames_end
+#define NOFRAMES(c, name) do { if ((c)->frames_n) return fail((c), VCRT_ERR_STATE, std::string(name) + ": frames are in flight (call vcrt_frames_end first)"); } while (0)
+
 int vcrt_fail(vcrt_ctx* c, int code, const std::string& msg) { return fail(c, code, msg); }
 int vcrt_cuda_fail(vcrt_ctx* c, cudaError_t e, const char* what) { return cuda_fail(c, e, what); }
 static int ensure(vcrt_ctx* c, DevBuf& b, size_t bytes, const char* what);
@@ -172,6 +175,7 @@ int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
 
 int vcrt_set_stream(vcrt_ctx* c, void* cuda_stream) {
     if (!c) return VCRT_ERR_INVALID;
+    NOFRAMES(c, "vcrt_set_stream");
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, cudaStreamSynchronize(c->stream), "synchronize");
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
@@ -189,6 +193,14 @@ int vcrt_destroy(vcrt_ctx* c) {
         if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
     }
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    for (FrameSlot& fs : c->frame_slot) {
+        if (fs.stream) { cudaStreamSynchronize(fs.stream); cudaStreamDestroy(fs.stream); }
+        if (fs.folded) cudaEventDestroy(fs.folded);
+        if (fs.done) cudaEventDestroy(fs.done);
+        if (fs.image.ptr) cudaFree(fs.image.ptr);
+        if (fs.sample.ptr) cudaFree(fs.sample.ptr);
+        if (fs.counter) cudaFree(fs.counter);
+    }
     c->trace_timer.destroy();
     for (auto& b : c->ssbo) if (b.ptr) cudaFree(b.ptr);
     for (DevBuf* b : {&c->fnodes, &c->ftris, &c->target, &c->accum8, &c->accumf, &c->aov, &c->wf_q0, &c->wf_q1, &c->wf_hit, &c->wf_color, &c->wf_counts, &c->qnodes, &c->q4nodes, &c->present}) if (b->ptr) cudaFree(b->ptr);
@@ -217,6 +229,7 @@ static int set_buffer_common(vcrt_ctx* c, int binding, const void* src, size_t b
     if (bytes % kStride[binding] != 0) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: size is not a multiple of the record size");
     if (bytes / kStride[binding] > 0x7fffffffu) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: too many records");
     if (bytes && !src) return fail(c, VCRT_ERR_INVALID, "vcrt_set_buffer: NULL source");
+    NOFRAMES(c, "vcrt_set_buffer");
     CU(c, cudaSetDevice(c->device), "set device");
     int rc = ensure(c, c->ssbo[binding], bytes, "allocate storage buffer");
     if (rc) return rc;
@@ -235,6 +248,7 @@ int vcrt_set_buffer_device(vcrt_ctx* c, int binding, const void* dev, size_t byt
 
 int vcrt_clear_accum(vcrt_ctx* c) {
     if (!c) return VCRT_ERR_INVALID;
+    NOFRAMES(c, "vcrt_clear_accum");
     CU(c, cudaSetDevice(c->device), "set device");
     for (DevBuf* b : {&c->target, &c->accum8, &c->accumf, &c->aov, &c->present})
         if (b->ptr && b->bytes) CU(c, cudaMemsetAsync(b->ptr, 0, b->bytes, c->stream), "clear image");
@@ -244,6 +258,7 @@ int vcrt_clear_accum(vcrt_ctx* c) {
 int vcrt_set_image_size(vcrt_ctx* c, uint32_t w, uint32_t h) {
     if (!c) return VCRT_ERR_INVALID;
     if (w == 0 || h == 0 || w > 65536u || h > 65536u) return fail(c, VCRT_ERR_INVALID, "vcrt_set_image_size: bad extent");
+    NOFRAMES(c, "vcrt_set_image_size");
     CU(c, cudaSetDevice(c->device), "set device");
     const size_t npix = (size_t)w * h;
     int rc;
@@ -367,8 +382,14 @@ static int prepare_fast(vcrt_ctx* c) {
     return VCRT_OK;
 }
 
-static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW, uint32_t covH) {
+// fs != nullptr: a frame in flight (vcrt_frame_submit) -- everything goes onto the slot's stream, the one-launch kernels leave the
+// frame's sample in the slot's buffer instead of folding it (a.sample_out), the wavefront pipeline uses the slot's queue set and
+// orders its accumulate kernel behind the previous frame's fold; *out_args receives the kernel arguments for the fold kernel.
+static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW, uint32_t covH, FrameSlot* fs = nullptr, int fs_index = 0, bool restart = false,
+                         KernelArgs* out_args = nullptr) {
     if (c->W == 0) return fail(c, VCRT_ERR_STATE, "render: no storage images bound (vcrt_set_image_size)");
+    if (!fs) NOFRAMES(c, "render");
+    const cudaStream_t stream = fs ? fs->stream : c->stream;
     if (p.shader > VCRT_SHADER_SIMPLE || p.traversal > VCRT_TRAVERSAL_BRUTE_FORCE || p.rng_mode > VCRT_RNG_PHILOX || p.accum_mode > VCRT_ACCUM_F32 ||
         p.trig_mode > VCRT_TRIG_PORTABLE)
         return fail(c, VCRT_ERR_INVALID, "render: enum field out of range");
@@ -399,9 +420,11 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     }
 
     setup_args(a, c->ubo, p, c->W, c->H, covW, covH, s.nlights);
+    a.flags &= ~VCRT_FLAG_INTERNAL_RESTART;
+    if (restart) a.flags |= VCRT_FLAG_INTERNAL_RESTART;
     a.target = (uchar4*)c->target.ptr; a.accum8 = (uchar4*)c->accum8.ptr; a.accumf = (float4*)c->accumf.ptr; a.aov = (vcrt_aov*)c->aov.ptr;
     a.counters = c->d_counters;
-    a.work_counter = (unsigned int*)(c->d_counters + 3);
+    a.work_counter = fs ? (unsigned int*)fs->counter : (unsigned int*)(c->d_counters + 3);
     a.leaf_threshold = c->leaf_threshold; a.shade_threshold = c->shade_threshold; a.continue_threshold = c->continue_threshold;
 
     // timing events come from a pool (a frame loop renders thousands of frames: no event creation in steady state)
@@ -412,7 +435,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     }
     auto give_back = [&]() { c->ev_pool.push_back(e0); c->ev_pool.push_back(e1); };
     cudaError_t e;
-    if ((e = cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream)) != cudaSuccess || (e = cudaEventRecord(e0, c->stream)) != cudaSuccess) {
+    if ((e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream)) != cudaSuccess || (e = cudaEventRecord(e0, stream)) != cudaSuccess) {
         give_back();
         return cuda_fail(c, e, "start render");
     }
@@ -425,9 +448,16 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     // (~0.27 ms per bounce on C3 whatever the ray count), and eight such tails in a row cost more than the megakernel's lower lane
     // utilisation: 1.82 vs 2.09 ms per 1080p frame on C3, 0.84 vs 1.10 ms on the bundled scene (profiles/r02_v6_latency_*.log).
     bool one_launch = (p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL)) != 0;
+    // With two or more frames in flight (vcrt_frame_submit) the tails overlap the next frames' work anyway, and what counts is the
+    // work per frame: on a large scene the wavefront pipeline needs half the megakernel's (C3, depth 8, 1080p: 1.40 / 1.25 / 1.18 ms per
+    // frame with 2 / 3 / 4 frames in flight against the megakernel's 1.57 / 1.47 / 1.47; on the bundled 2 K-triangle scene the
+    // megakernel's single launch stays ahead: 0.72 / 0.60 / 0.60 against 0.76 / 0.68 / 0.64 -- profiles/r02_v11_latency_*.log).
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && !(p.flags & VCRT_FLAG_WAVEFRONT) && a.sample_count == 1u) {
-        a.flags |= a.env.max_bounces <= 4u ? VCRT_FLAG_STATIC_KERNEL : VCRT_FLAG_MEGAKERNEL;
-        one_launch = true;
+        const bool deep = a.env.max_bounces > 4u;
+        if (!(deep && fs && c->frames_n >= 2 && s.ntris >= 65536u)) {
+            a.flags |= deep ? VCRT_FLAG_MEGAKERNEL : VCRT_FLAG_STATIC_KERNEL;
+            one_launch = true;
+        }
     }
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch) {
         // wavefront pipeline: a batch = a range of pixels x all samples of the call; queues sized for what the call needs, at most
@@ -437,8 +467,8 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
         // small frame lasts as long as its longest ray (~0.2 ms) whatever its size, and four times as many launches cost more
         // than the overlap returns.
         const uint64_t need = (uint64_t)a.owned_tiles * 1024u * a.sample_count;
-        int sets = c->wf_streams ? c->wf_streams : 1;
-        uint64_t per_set = (need + (uint64_t)sets - 1) / (uint64_t)sets;
+        int sets = fs ? c->frames_n : c->wf_streams ? c->wf_streams : 1;   // frames in flight: one queue set per slot
+        uint64_t per_set = fs ? need : (need + (uint64_t)sets - 1) / (uint64_t)sets;   // a frame in flight is one pipeline
         per_set = (per_set + a.sample_count - 1) / a.sample_count * a.sample_count;   // whole pixels
         if (per_set > c->wf_batch) per_set = c->wf_batch;
         uint32_t want = (uint32_t)per_set;
@@ -446,6 +476,8 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
         if (want < 1024u) want = 1024u;
         int rc = VCRT_OK;
         if (c->wf_capacity != want || c->wf_sets != sets) {
+            for (int i = 0; i < c->frames_n; ++i)   // the queues are about to move: no frame in flight may still be using them
+                if ((e = cudaStreamSynchronize(c->frame_slot[i].stream)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "synchronize"); }
             const size_t n = (size_t)want * (size_t)sets;
             if ((rc = ensure(c, c->wf_q0, n * 48, "allocate ray queue")) || (rc = ensure(c, c->wf_q1, n * 48, "allocate ray queue")) ||
                 (rc = ensure(c, c->wf_hit, n * 8, "allocate hit buffer")) || (rc = ensure(c, c->wf_color, n * 16, "allocate sample buffer")) ||
@@ -454,30 +486,39 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
         }
         WfPipes pipes;
         std::memset(&pipes, 0, sizeof pipes);
-        pipes.n = sets;
-        pipes.stream[0] = c->stream;
-        for (int i = 0; i < sets; ++i) {
+        auto queue_set = [&](int i) {
+            WfQueues q;
+            q.q[0] = (float4*)c->wf_q0.ptr + (size_t)i * want * 3; q.q[1] = (float4*)c->wf_q1.ptr + (size_t)i * want * 3;
+            q.hit = (uint2*)c->wf_hit.ptr + (size_t)i * want; q.sample_color = (float4*)c->wf_color.ptr + (size_t)i * want;
+            q.counts = (unsigned int*)c->wf_counts.ptr + 16 * i;
+            q.capacity = want;
+            return q;
+        };
+        pipes.n = fs ? 1 : sets;
+        pipes.stream[0] = stream;
+        if (fs) { pipes.q[0] = queue_set(fs_index); pipes.before_accumulate = c->last_folded; }
+        for (int i = 0; i < (fs ? 0 : sets); ++i) {
             if (i > 0) {
                 if (!c->pipe_stream[i] && (e = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create pipeline stream"); }
                 if (!c->join_ev[i] && (e = cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create event"); }
                 pipes.stream[i] = c->pipe_stream[i];
                 pipes.join[i] = c->join_ev[i];
             }
-            WfQueues& q = pipes.q[i];
-            q.q[0] = (float4*)c->wf_q0.ptr + (size_t)i * want * 3; q.q[1] = (float4*)c->wf_q1.ptr + (size_t)i * want * 3;
-            q.hit = (uint2*)c->wf_hit.ptr + (size_t)i * want; q.sample_color = (float4*)c->wf_color.ptr + (size_t)i * want;
-            q.counts = (unsigned int*)c->wf_counts.ptr + 16 * i;
-            q.capacity = want;
+            pipes.q[i] = queue_set(i);
         }
-        if (sets > 1 && !c->fork_ev && (e = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create event"); }
+        if (!fs && sets > 1 && !c->fork_ev && (e = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create event"); }
         pipes.fork = c->fork_ev;
         nlaunch = 0;
         e = launch_render_wavefront(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, pipes, &nlaunch, &c->trace_timer);
-    } else if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
-    else if (p.traversal == VCRT_TRAVERSAL_BRUTE_FORCE) e = launch_render_brute(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
-    else e = launch_render_reference(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, c->stream);
+    } else {
+        if (fs) a.sample_out = (float4*)fs->sample.ptr;   // one launch: the sample is handed to the fold kernel
+        if (p.traversal == VCRT_TRAVERSAL_FAST) e = launch_render_fast(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, stream);
+        else if (p.traversal == VCRT_TRAVERSAL_BRUTE_FORCE) e = launch_render_brute(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, stream);
+        else e = launch_render_reference(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, stream);
+    }
     if (e != cudaSuccess) { give_back(); return cuda_fail(c, e, "launch render kernel"); }
-    if ((e = cudaEventRecord(e1, c->stream)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "record event"); }
+    if ((e = cudaEventRecord(e1, stream)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "record event"); }
+    if (out_args) *out_args = a;
     c->events.emplace_back(e0, e1);
     c->launches += nlaunch;
     if (c->events.size() >= 256 || c->trace_timer.pending.size() >= 2048) harvest_events(c);   // a frame loop that never asks for counters
@@ -491,10 +532,8 @@ int vcrt_render(vcrt_ctx* c, const vcrt_render_params* p) {
     return render_common(c, *p, ref_cov ? (c->W / 32) * 32 : c->W, ref_cov ? (c->H / 32) * 32 : c->H);
 }
 
-int vcrt_dispatch(vcrt_ctx* c, uint32_t gx, uint32_t gy, uint32_t gz) {
-    if (!c) return VCRT_ERR_INVALID;
-    if (gz == 0 || gx == 0 || gy == 0) return VCRT_OK;   // vkCmdDispatch with a zero dimension does nothing
-    vcrt_render_params p;
+// What ComputeModel::computeCommand renders, as render parameters (shared by vcrt_dispatch and vcrt_frame_dispatch).
+static int dispatch_params(vcrt_ctx* c, uint32_t gx, uint32_t gy, vcrt_render_params& p, uint32_t& covW, uint32_t& covH) {
     std::memset(&p, 0, sizeof p);
     p.struct_size = sizeof p;
     p.shader = (uint32_t)c->shader;
@@ -522,13 +561,27 @@ int vcrt_dispatch(vcrt_ctx* c, uint32_t gx, uint32_t gy, uint32_t gz) {
     p.sample_begin = c->ubo.currentSample;
     p.sample_count = 1;
     const uint64_t cw = (uint64_t)gx * 32u, ch = (uint64_t)gy * 32u;   // invocations beyond the image neither load nor store
-    return render_common(c, p, (uint32_t)(cw < c->W ? cw : c->W), (uint32_t)(ch < c->H ? ch : c->H));
+    covW = (uint32_t)(cw < c->W ? cw : c->W);
+    covH = (uint32_t)(ch < c->H ? ch : c->H);
+    return VCRT_OK;
+}
+
+int vcrt_dispatch(vcrt_ctx* c, uint32_t gx, uint32_t gy, uint32_t gz) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (gz == 0 || gx == 0 || gy == 0) return VCRT_OK;   // vkCmdDispatch with a zero dimension does nothing
+    NOFRAMES(c, "vcrt_dispatch");
+    vcrt_render_params p;
+    uint32_t covW, covH;
+    int rc = dispatch_params(c, gx, gy, p, covW, covH);
+    if (rc) return rc;
+    return render_common(c, p, covW, covH);
 }
 
 int vcrt_resolve(vcrt_ctx* c, uint32_t total_samples, float gamma) {
     if (!c) return VCRT_ERR_INVALID;
     if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_resolve: no storage images bound");
     if (total_samples == 0) return fail(c, VCRT_ERR_INVALID, "vcrt_resolve: total_samples is 0");
+    NOFRAMES(c, "vcrt_resolve");
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, launch_resolve((const float4*)c->accumf.ptr, (uchar4*)c->target.ptr, c->W * c->H, 1.0f / (float)total_samples, gamma > 0.0f ? 1.0f / gamma : 0.0f, c->stream),
        "launch resolve kernel");
@@ -541,6 +594,7 @@ int vcrt_post_process(vcrt_ctx* c, float mix, float sigma, float k_sigma, float 
     if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_post_process: no storage images bound");
     if (mix != 0.0f && (!(sigma > 0.0f) || !(k_sigma >= 0.0f) || !(threshold > 0.0f) || k_sigma * sigma > 64.0f))
         return fail(c, VCRT_ERR_INVALID, "vcrt_post_process: need sigma > 0, kSigma >= 0, threshold > 0, kSigma * sigma <= 64");
+    NOFRAMES(c, "vcrt_post_process");
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, launch_post_process((const uchar4*)c->target.ptr, (uchar4*)c->present.ptr, c->W, c->H, mix, sigma, k_sigma, threshold, gamma > 0.0f ? 1.0f / gamma : 0.0f, c->stream),
        "launch post-process kernel");
@@ -558,6 +612,7 @@ static int tiles_common(vcrt_ctx* c, int what, uint32_t rank, uint32_t count, vo
     const uint32_t owned = tiles > rank ? (tiles - rank + count - 1) / count : 0u;
     const size_t elem = what == 0 ? 4 : 16;
     if (!packed || bytes < (size_t)owned * 1024u * elem) return fail(c, VCRT_ERR_INVALID, "tiles: packed buffer smaller than owned_tiles * 1024 * element size");
+    NOFRAMES(c, "tiles");
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, launch_tiles(what == 0 ? c->target.ptr : c->accumf.ptr, packed, (int)elem, pack, c->W, c->H, rank, count, owned, c->stream), "launch tile kernel");
     c->launches += owned ? 1 : 0;
@@ -575,6 +630,7 @@ static int read_common(vcrt_ctx* c, const DevBuf& b, void* dst, size_t bytes, co
     if (!c) return VCRT_ERR_INVALID;
     if (c->W == 0) return fail(c, VCRT_ERR_STATE, std::string(what) + ": no storage images bound");
     if (!dst || bytes != b.bytes) return fail(c, VCRT_ERR_INVALID, std::string(what) + ": size mismatch");
+    NOFRAMES(c, what);
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, cudaMemcpyAsync(dst, b.ptr, bytes, cudaMemcpyDeviceToHost, c->stream), what);
     CU(c, cudaStreamSynchronize(c->stream), what);
@@ -591,6 +647,7 @@ int vcrt_write_accum_f32(vcrt_ctx* c, const void* src, size_t bytes) {
     if (!c) return VCRT_ERR_INVALID;
     if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_write_accum_f32: no storage images bound");
     if (!src || bytes != c->accumf.bytes) return fail(c, VCRT_ERR_INVALID, "vcrt_write_accum_f32: size mismatch");
+    NOFRAMES(c, "vcrt_write_accum_f32");
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, cudaMemcpyAsync(c->accumf.ptr, src, bytes, cudaMemcpyHostToDevice, c->stream), "write f32 accumulation");
     CU(c, cudaStreamSynchronize(c->stream), "synchronize");
@@ -607,15 +664,129 @@ int vcrt_device_ptr(vcrt_ctx* c, int what, void** out, size_t* bytes) {
     return VCRT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- frames in flight (include/vcrt.h)
+int vcrt_frames_begin(vcrt_ctx* c, uint32_t n) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (n < 1 || n > VCRT_MAX_FRAMES_IN_FLIGHT) return fail(c, VCRT_ERR_INVALID, "vcrt_frames_begin: frames_in_flight must be 1..4");
+    if (c->W == 0) return fail(c, VCRT_ERR_STATE, "vcrt_frames_begin: no storage images bound (vcrt_set_image_size)");
+    NOFRAMES(c, "vcrt_frames_begin");
+    CU(c, cudaSetDevice(c->device), "set device");
+    CU(c, cudaStreamSynchronize(c->stream), "synchronize");   // the slots' streams start from a quiet context
+    const size_t npix = (size_t)c->W * c->H;
+    for (uint32_t i = 0; i < n; ++i) {
+        FrameSlot& fs = c->frame_slot[i];
+        if (!fs.stream) CU(c, cudaStreamCreateWithFlags(&fs.stream, cudaStreamNonBlocking), "create frame stream");
+        if (!fs.folded) CU(c, cudaEventCreateWithFlags(&fs.folded, cudaEventDisableTiming), "create event");
+        if (!fs.done) CU(c, cudaEventCreateWithFlags(&fs.done, cudaEventDisableTiming), "create event");
+        if (!fs.counter) CU(c, cudaMalloc((void**)&fs.counter, 2 * sizeof(unsigned long long)), "allocate work counter");
+        int rc;
+        if ((rc = ensure(c, fs.image, npix * 4, "allocate frame image")) || (rc = ensure(c, fs.sample, npix * 16, "allocate frame sample buffer"))) return rc;
+        fs.busy = false;
+    }
+    c->frames_n = (int)n;
+    c->frame_next = 0;
+    c->last_folded = nullptr;
+    return VCRT_OK;
+}
+
+int vcrt_frame_wait(vcrt_ctx* c, uint32_t slot) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (!c->frames_n || slot >= (uint32_t)c->frames_n) return fail(c, VCRT_ERR_INVALID, "vcrt_frame_wait: no such frame slot");
+    FrameSlot& fs = c->frame_slot[slot];
+    if (fs.busy) {
+        CU(c, cudaSetDevice(c->device), "set device");
+        CU(c, cudaEventSynchronize(fs.done), "wait for frame");
+        fs.busy = false;
+    }
+    return VCRT_OK;
+}
+
+static int frame_submit_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW, uint32_t covH, uint32_t total_samples, float gamma, void* host_dst, size_t bytes,
+                               uint32_t* slot_out) {
+    if (host_dst && bytes != (size_t)c->W * c->H * 4) return fail(c, VCRT_ERR_INVALID, "frame submit: size mismatch");
+    const uint32_t slot = c->frame_next;
+    FrameSlot& fs = c->frame_slot[slot];
+    int rc = vcrt_frame_wait(c, slot);   // main.cpp:325: wait for the fence of the slot about to be reused
+    if (rc) return rc;
+    CU(c, cudaSetDevice(c->device), "set device");
+    const bool restart = p.accum_mode == VCRT_ACCUM_F32 && p.sample_begin == 0;
+    KernelArgs a;
+    if ((rc = render_common(c, p, covW, covH, &fs, (int)slot, restart, &a))) return rc;
+    // fold in frame order.  One-launch kernels: the sample waits in the slot's buffer, the fold kernel applies it behind the previous
+    // frame's fold.  Wavefront pipeline: its accumulate kernel already waited for that event; what is left is the resolve.
+    if (a.sample_out && c->last_folded) CU(c, cudaStreamWaitEvent(fs.stream, c->last_folded, 0), "order frame folds");
+    const float inv_total = 1.0f / (float)(total_samples ? total_samples : p.sample_begin + 1u);
+    CU(c, launch_frame_fold(a, a.sample_out, (uchar4*)fs.image.ptr, inv_total, gamma > 0.0f ? 1.0f / gamma : 0.0f, fs.stream), "launch fold kernel");
+    CU(c, cudaEventRecord(fs.folded, fs.stream), "record event");
+    c->last_folded = fs.folded;
+    if (host_dst) CU(c, cudaMemcpyAsync(host_dst, fs.image.ptr, bytes, cudaMemcpyDeviceToHost, fs.stream), "read frame back");
+    CU(c, cudaEventRecord(fs.done, fs.stream), "record event");
+    fs.busy = true;
+    c->launches += 1;
+    c->frame_next = (slot + 1u) % (uint32_t)c->frames_n;
+    if (slot_out) *slot_out = slot;
+    return VCRT_OK;
+}
+
+int vcrt_frame_submit(vcrt_ctx* c, const vcrt_render_params* p, uint32_t total_samples, float gamma, void* host_dst, size_t bytes, uint32_t* slot_out) {
+    if (!c || !p) return fail(c, VCRT_ERR_INVALID, "vcrt_frame_submit: NULL argument");
+    if (p->struct_size != sizeof(vcrt_render_params)) return fail(c, VCRT_ERR_INVALID, "vcrt_frame_submit: struct_size mismatch");
+    if (!c->frames_n) return fail(c, VCRT_ERR_STATE, "vcrt_frame_submit: call vcrt_frames_begin first");
+    if (p->sample_count > 1) return fail(c, VCRT_ERR_INVALID, "vcrt_frame_submit: a frame in flight renders one sample per pixel (sample_count 0 or 1)");
+    const bool ref_cov = (p->flags & VCRT_FLAG_REF_DISPATCH_COVERAGE) != 0;
+    return frame_submit_common(c, *p, ref_cov ? (c->W / 32) * 32 : c->W, ref_cov ? (c->H / 32) * 32 : c->H, total_samples, gamma, host_dst, bytes, slot_out);
+}
+
+int vcrt_frame_dispatch(vcrt_ctx* c, uint32_t gx, uint32_t gy, uint32_t gz, void* host_dst, size_t bytes, uint32_t* slot_out) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (!c->frames_n) return fail(c, VCRT_ERR_STATE, "vcrt_frame_dispatch: call vcrt_frames_begin first");
+    vcrt_render_params p;
+    uint32_t covW, covH;
+    int rc = dispatch_params(c, gx, gy, p, covW, covH);
+    if (rc) return rc;
+    if (gz == 0 || gx == 0 || gy == 0) covW = covH = 0;   // vkCmdDispatch with a zero dimension renders nothing; the frame is still presented
+    return frame_submit_common(c, p, covW, covH, 0, 0.0f, host_dst, bytes, slot_out);
+}
+
+int vcrt_frames_end(vcrt_ctx* c) {
+    if (!c) return VCRT_ERR_INVALID;
+    if (!c->frames_n) return VCRT_OK;
+    CU(c, cudaSetDevice(c->device), "set device");
+    for (int i = 0; i < c->frames_n; ++i) {
+        CU(c, cudaStreamSynchronize(c->frame_slot[i].stream), "synchronize");
+        c->frame_slot[i].busy = false;
+    }
+    c->frames_n = 0;
+    c->last_folded = nullptr;
+    return VCRT_OK;
+}
+
+int vcrt_alloc_host(size_t bytes, void** out) {
+    if (!out) return VCRT_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "allocate page-locked host memory");
+    return VCRT_OK;
+}
+
+int vcrt_free_host(void* ptr) {
+    if (!ptr) return VCRT_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "free page-locked host memory");
+    return VCRT_OK;
+}
+
 int vcrt_synchronize(vcrt_ctx* c) {
     if (!c) return VCRT_ERR_INVALID;
     CU(c, cudaSetDevice(c->device), "set device");
     CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+    for (int i = 0; i < c->frames_n; ++i) CU(c, cudaStreamSynchronize(c->frame_slot[i].stream), "synchronize");
     return VCRT_OK;
 }
 
 static int drain_events(vcrt_ctx* c) {
     CU(c, cudaStreamSynchronize(c->stream), "synchronize");
+    for (int i = 0; i < c->frames_n; ++i) CU(c, cudaStreamSynchronize(c->frame_slot[i].stream), "synchronize");   // frames in flight record their events on the slots' streams
     for (auto& ev : c->events) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) c->kernel_ms += ms;

@@ -15,8 +15,22 @@ struct DevBuf {
     size_t capacity = 0;
 };
 
+// One frame in flight (vcrt_frame_submit): its own stream, sample buffer, rgba8 image and work counter, so that the render kernels of
+// consecutive frames overlap; `folded` orders the folds of consecutive frames, `done` is the fence the host waits on (main.cpp:325).
+struct FrameSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t folded = nullptr, done = nullptr;
+    DevBuf image, sample;
+    unsigned long long* counter = nullptr;
+    bool busy = false;
+};
+
 struct vcrt_ctx {
     int device = 0;
+    FrameSlot frame_slot[VCRT_MAX_FRAMES_IN_FLIGHT];
+    int frames_n = 0;                     // frames in flight between vcrt_frames_begin and vcrt_frames_end (0: the synchronous interface is in use)
+    uint32_t frame_next = 0;              // slot of the next vcrt_frame_submit
+    cudaEvent_t last_folded = nullptr;    // `folded` of the most recently submitted frame
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     std::string error;

@@ -178,6 +178,7 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, const WfPipes& pipes,
             *launches += 3;
             b.cur ^= 1u;
         }
+        if (pipes.before_accumulate && bi == 0 && (e = cudaStreamWaitEvent(stream, pipes.before_accumulate, 0)) != cudaSuccess) return e;   // frames in flight: fold in frame order
         wf_accumulate_kernel<<<(b.nitems + 255u) / 256u, 256, 0, stream>>>(a, w, b);
         ++*launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -26,6 +26,7 @@ struct WfPipes {
     cudaStream_t stream[VCRT_MAX_PIPES];
     WfQueues q[VCRT_MAX_PIPES];
     cudaEvent_t fork, join[VCRT_MAX_PIPES];
+    cudaEvent_t before_accumulate;   // frames in flight: the accumulate kernel waits for this event (the previous frame's fold); nullptr = none
 };
 
 // CUDA events around every launch of the dominant kernel (wf_trace_kernel), recorded on the launching stream, so that the
@@ -87,4 +88,5 @@ cudaError_t launch_unpack_all_tiles(void* image, const void* gathered, int elem_
 cudaError_t launch_post_process(const uchar4* tex, uchar4* out, uint32_t w, uint32_t h, float mix, float sigma, float kSigma, float threshold, float inv_gamma,
                                 cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accumf, uchar4* target, uint32_t npix, float inv_total, float inv_gamma, cudaStream_t stream);
+cudaError_t launch_frame_fold(const KernelArgs& a, const float4* sample, uchar4* image, float inv_total, float inv_gamma, cudaStream_t stream);
 }  // namespace vcrt

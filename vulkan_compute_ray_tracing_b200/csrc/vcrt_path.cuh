@@ -26,7 +26,12 @@ struct KernelArgs {
     unsigned int* work_counter;          // persistent kernels: next work item
     uint32_t leaf_threshold, shade_threshold;   // persistent kernel phase thresholds (lanes)
     uint32_t continue_threshold;                // trace kernel: lanes on inner nodes at or above which the phase votes are skipped
+    float4* sample_out;                  // frames in flight (vcrt_frame_submit): the one-launch kernels store the frame's sample colour here, per pixel,
+                                         // instead of folding it into the accumulation -- the fold happens in frame order (vcrt_post.cu: frame_fold_kernel)
 };
+
+// internal flag (not part of the C ABI's VCRT_FLAG_*): the accumulation of the covered pixels restarts with this call's samples
+#define VCRT_FLAG_INTERNAL_RESTART 0x80000000u
 
 // Work item -> pixel.  Items enumerate the owned 32x32 tiles; inside a tile, 32 consecutive items form an
 // 8x4 pixel block so that a warp's primary rays are coherent.  Returns false for pixels outside the coverage.
@@ -88,6 +93,13 @@ VCRT_HD void render_pixel(const KernelArgs& a, uint32_t x, uint32_t y, TraceStat
     const bool f32 = a.accum_mode == VCRT_ACCUM_F32;
     float4 acc = make_float4(0, 0, 0, 0);
     uchar4 px = make_uchar4(0, 0, 0, 0);
+    if (a.sample_out) {   // a frame in flight (one sample): hand the colour over, the fold runs in frame order
+        Rng g;
+        rng_init<RNG_MODE>(g, x, y, (uint32_t)pix, a.sample_begin, a.philox_seed);
+        const float3 c = ray_color<SHADER, TRAV, RNG_MODE, TRIG, COUNT>(a, primary, g, st, (a.flags & VCRT_FLAG_WRITE_AOV) ? &a.aov[pix] : nullptr);
+        a.sample_out[pix] = make_float4(c.x, c.y, c.z, 1.0f);
+        return;
+    }
     if (f32) acc = a.accumf[pix];
     else px = a.accum8[pix];
     for (uint32_t k = 0; k < a.sample_count; ++k) {

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
                     else running_mean_rgba8(px8, thr, a.sample_begin + k);
                     k++;
                     if (k == a.sample_count) {
-                        if (f32) a.accumf[pix] = acc;
+                        if (a.sample_out) a.sample_out[pix] = make_float4(thr.x, thr.y, thr.z, 1.0f);   // a frame in flight (one sample): folded in frame order later
+                        else if (f32) a.accumf[pix] = acc;
                         else { a.target[pix] = px8; a.accum8[pix] = px8; }
                         has_pixel = false;
                     }
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_MEGA_MINB) render_persistent
                     has_pixel = true;
                     pix = y * a.W + x;
                     k = 0;
-                    if (f32) acc = a.accumf[pix]; else px8 = a.accum8[pix];
+                    if (!a.sample_out) { if (f32) acc = a.accumf[pix]; else px8 = a.accum8[pix]; }
                 }
             }
             have_ray = !done;

@@ -146,6 +146,60 @@ cudaError_t launch_post_process(const uchar4* tex, uchar4* out, uint32_t w, uint
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- frames in flight
+// The fold of one frame in flight (vcrt_frame_submit; the reference keeps MAX_FRAMES_IN_FLIGHT = 2 frames going, main.cpp:68,
+// :298-316, :325, :394): the render kernels of consecutive frames overlap on their own streams and leave the frame's one sample
+// per pixel in `sample`; this kernel, ordered behind the previous frame's fold by an event, applies it to the accumulation
+// exactly as the render kernels do in the synchronous path (f32: acc += c, w += 1 -- ray-trace-compute.comp:375-379 for the
+// rgba8 running mean), resolves the pixel (resolve_kernel's arithmetic) and writes it to the target and to the frame's own
+// rgba8 image, which is what travels to the host while the next frames render.  sample == nullptr: the accumulation is already
+// up to date (wavefront pipeline: its accumulate kernel ran behind the same event); only resolve / copy.
+__global__ void __launch_bounds__(256) frame_fold_kernel(const __grid_constant__ KernelArgs a, const float4* __restrict__ sample, uchar4* __restrict__ image,
+                                                         float inv_total, float inv_gamma) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= a.W * a.H) return;
+    const uint32_t y = i / a.W, x = i - y * a.W;
+    const uint32_t tile = (y >> 5) * a.tilesX + (x >> 5);
+    const bool covered = sample != nullptr && x < a.covW && y < a.covH && tile % a.tile_count == a.tile_rank;
+    uchar4 px;
+    if (a.accum_mode == VCRT_ACCUM_F32) {
+        float4 acc = a.accumf[i];
+        if (covered) {
+            const float4 c = sample[i];
+            if (a.flags & VCRT_FLAG_INTERNAL_RESTART) acc = make_float4(0, 0, 0, 0);
+            acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += 1.0f;
+            a.accumf[i] = acc;
+        }
+        const float cc[4] = {acc.x * inv_total, acc.y * inv_total, acc.z * inv_total, acc.w * inv_total};
+        uint8_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = cc[k];
+            v = !(v == v) ? 0.0f : (v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v));
+            if (inv_gamma > 0.0f && k < 3) v = powf(v, inv_gamma);
+            o[k] = (uint8_t)rintf(v * 255.0f);
+        }
+        px = make_uchar4(o[0], o[1], o[2], o[3]);
+        a.target[i] = px;
+    } else if (covered) {
+        const float4 c = sample[i];
+        px = a.accum8[i];
+        running_mean_rgba8(px, make_float3(c.x, c.y, c.z), a.sample_begin);
+        a.target[i] = px;
+        a.accum8[i] = px;
+    } else {
+        px = a.target[i];
+    }
+    image[i] = px;
+}
+
+cudaError_t launch_frame_fold(const KernelArgs& a, const float4* sample, uchar4* image, float inv_total, float inv_gamma, cudaStream_t stream) {
+    const uint32_t npix = a.W * a.H;
+    if (npix == 0) return cudaSuccess;
+    frame_fold_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(a, sample, image, inv_total, inv_gamma);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(const float4* accumf, uchar4* target, uint32_t npix, float inv_total, float inv_gamma, cudaStream_t stream) {
     if (npix == 0) return cudaSuccess;
     resolve_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(accumf, target, npix, inv_total, inv_gamma);

@@ -301,8 +301,9 @@ __global__ void __launch_bounds__(256) wf_accumulate_kernel(const __grid_constan
     if (!item_to_pixel(a, b.item0 + it, x, y)) return;
     const uint32_t pix = y * a.W + x;
     const float4* c = w.sample_color + (size_t)it * a.sample_count;
+    const bool restart = (a.flags & VCRT_FLAG_INTERNAL_RESTART) != 0u;   // frames in flight: the accumulation starts over with this frame
     if (a.accum_mode == VCRT_ACCUM_F32) {
-        float4 acc = a.accumf[pix];
+        float4 acc = restart ? make_float4(0, 0, 0, 0) : a.accumf[pix];
         for (uint32_t k = 0; k < a.sample_count; ++k) { const float4 v = stream_ld(c + k); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += 1.0f; }
         a.accumf[pix] = acc;
     } else {

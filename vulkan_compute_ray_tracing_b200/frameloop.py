@@ -6,6 +6,7 @@ restarts on every camera move, one dispatch per frame, `ms/frame` statistics.
   updateScene       src/main.cpp:166-183        hasMoved -> currentSample = 0; write the 32-byte UBO; currentSample++
   drawFrame         src/main.cpp:323-395        -> ComputeModel.computeCommand(cmd, frame, W/32, H/32, 1)
   mainLoop          src/main.cpp:399-421        prints "%f ms/frame" once per second of frames
+  frames in flight  src/main.cpp:68, :298-316, :325, :394   MAX_FRAMES_IN_FLIGHT = 2 slots, each behind a fence: FrameLoop(frames_in_flight=2)
 
 Key presses come from a script (a string, one character per frame: w a s d u(p) j(down) . = no key) instead of GLFW.
 """
@@ -50,8 +51,17 @@ class FrameLoop:
     """mainLoop/drawFrame of main.cpp around a ComputeModel.  `frame_time` is the deltaTime fed to the camera (the reference
     uses wall-clock frame time; a fixed value makes scripted runs reproducible)."""
 
-    def __init__(self, model, scene, width, height, camera=None, frame_time=1.0 / 60.0, full_cover=True):
+    def __init__(self, model, scene, width, height, camera=None, frame_time=1.0 / 60.0, full_cover=True, frames_in_flight=0, on_present=None):
+        """frames_in_flight = 0: every drawFrame is a synchronous-interface computeCommand (asynchronous on the context's one stream;
+        nothing is read back until run() returns).  frames_in_flight = n >= 1: the reference's pipelined loop -- drawFrame waits for
+        the fence of the slot it reuses (main.cpp:325), submits the frame on that slot's stream and moves on (:394); every frame's
+        rgba8 image lands in the slot's page-locked buffer and `on_present(frame_index, array)` is called with it once its fence has
+        signalled (the presentation of main.cpp:382-392), in frame order.  Frames are bit-identical either way."""
         self.model, self.scene = model, scene
+        self.frames_in_flight = int(frames_in_flight)
+        self.on_present = on_present
+        self._slots = []            # per slot: [PinnedFrame, index of the frame in flight on it or None]
+        self._width, self._height = width, height
         self.camera = camera or Camera()
         self.frame_time = frame_time
         self.gx = (width + 31) // 32 if full_cover else width // 32      # main.cpp:228 dispatches floor(W/32) x floor(H/32)
@@ -69,7 +79,10 @@ class FrameLoop:
         ubo = self.model.getMaterial().getUniformBufferBundles()[0].data.buffers[0]
         ubo.write(pack_ubo(tuple(float(x) for x in self.camera.Position), self.currentSample, self.scene, time=0.0))
         self.currentSample += 1                                 # main.cpp:182
-        self.model.computeCommand(None, 0, self.gx, self.gy, 1)
+        if self.frames_in_flight:
+            self._draw_in_flight()
+        else:
+            self.model.computeCommand(None, 0, self.gx, self.gy, 1)
         self.frames += 1
         now = time.perf_counter()
         if self._t_last is None:
@@ -79,10 +92,46 @@ class FrameLoop:
             self.ms_per_frame.append(1000.0 * (now - self._t_last) / self._n_last)
             self._t_last, self._n_last = now, 0
 
+    # ---- the pipelined loop (frames_in_flight >= 1)
+    def _begin(self):
+        from .api import PinnedFrame
+        self.model.getMaterial().framesBegin(self.frames_in_flight)
+        self._slots = [[PinnedFrame(self._width, self._height), None] for _ in range(self.frames_in_flight)]
+        self._next = 0
+
+    def _retire(self, slot):
+        buf, idx = self._slots[slot]
+        if idx is not None:
+            self.model.getMaterial().frameWait(slot)            # vkWaitForFences(inFlightFences[currentFrame]), main.cpp:325
+            if self.on_present:
+                self.on_present(idx, buf.array)
+            self._slots[slot][1] = None
+
+    def _draw_in_flight(self):
+        if not self._slots:
+            self._begin()
+        slot = self._next
+        self._retire(slot)
+        got = self.model.frameCommand(None, 0, self.gx, self.gy, 1, out=self._slots[slot][0])
+        assert got == slot
+        self._slots[slot][1] = self.frames
+        self._next = (slot + 1) % self.frames_in_flight         # main.cpp:394
+
+    def finish(self):
+        """vkDeviceWaitIdle (main.cpp:419): retires the frames still in flight, in order, and leaves the pipelined mode."""
+        if self._slots:
+            for k in range(self.frames_in_flight):
+                self._retire((self._next + k) % self.frames_in_flight)
+            self.model.getMaterial().framesEnd()
+            for buf, _ in self._slots:
+                buf.free()
+            self._slots = []
+
     def run(self, script):
         """One frame per character of `script`; returns the final target image (H, W, 4) uint8."""
         for key in script:
             if key not in (FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN, NONE):
                 raise ValueError("unknown key %r in camera script" % key)
             self.drawFrame(key)
+        self.finish()
         return self.model.getMaterial().getStorageImages()[0].data.read()
