@@ -1,6 +1,8 @@
 // vcrt_launch.h -- host-visible launchers of the render kernels (one per traversal mode / translation unit).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 #include "vcrt_path.cuh"
@@ -54,9 +56,10 @@ struct TraceTimer {
     }
     // after a stream synchronise: total milliseconds and count of the pending launches; events go back to the pool
     void drain(double* ms, uint64_t* n) {
+        static const bool dump = getenv("VCRT_TRACE_DUMP") != nullptr;   // development aid: every trace launch's duration on stderr
         for (auto& p : pending) {
             float f = 0.0f;
-            if (cudaEventElapsedTime(&f, p.first, p.second) == cudaSuccess) { *ms += f; ++*n; if (p.primary) primary_ms += f; }
+            if (cudaEventElapsedTime(&f, p.first, p.second) == cudaSuccess) { *ms += f; ++*n; if (p.primary) primary_ms += f; if (dump) fprintf(stderr, "trace launch %s %.3f ms\n", p.primary ? "primary" : "bounce", f); }
             pool.push_back(p.first); pool.push_back(p.second);
         }
         pending.clear();

@@ -37,3 +37,12 @@
 #define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
 #endif
 
+/* r02 experiments that did not make it (logs under profiles/, code under tools/experiments/):
+ *   cache policy of the triangle-record loads (L2 evict-first / no hint / L1 no-allocate instead of L2 evict-last): +-1 % on C3 and on the
+ *     10 M-triangle scene, L1 no-allocate -3 % (r02_v12_ab_tri_policy.log);
+ *   ray binning -- the rays of the next bounce queued in the order of the grid cell (8^3..8^6 cells) that holds their origin, filed by a
+ *     warp-aggregated atomic per cell and placed directly by the shade kernel, no sort and no extra pass over the rays: the bounce
+ *     launches get 5-6 % faster on C3 (bounce 1, whose rays leave the shared primary hit points, gains nothing; bounce 7: -13 %) and 7 % on
+ *     the 10 M-triangle scene, but filing, scan and the shade kernel's scattered 48-byte stores cost more than that: 11.7 vs 11.1 ms at
+ *     16 spp, 43.3 vs 40.3 ms at 64 spp (r02_v21_ab_ray_binning.log).  A full radix sort of the queue (cub, 30-bit Morton key + a pass
+ *     that moves the rays) makes the bounce launches 15-19 % faster and the step 12 % slower (r02_v14_ab_ray_sort_potential.log). */
