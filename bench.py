@@ -265,6 +265,11 @@ class Probe:
         rc = self.lib.vcrt_probe_gather64(self.device, records_log2, steps, chains, reps, ctypes.byref(out))
         return out.value if rc == 0 else None
 
+    def gather128(self, records_log2, steps=32, chains=1, reps=3):
+        out = ctypes.c_double()
+        rc = self.lib.vcrt_probe_gather128(self.device, records_log2, steps, chains, reps, ctypes.byref(out))
+        return out.value if rc == 0 else None
+
     def stream(self, nbytes, passes=8, reps=3):
         out = ctypes.c_double()
         self.lib.vcrt_probe_stream.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
@@ -693,6 +698,9 @@ def main():
             # lane -- the ceiling is the rate HBM sustains once enough random reads are in flight, i.e. the largest of the three
             dram_gather64_by_chains = {ch: pr.gather64(25, steps=32 // ch, chains=ch) for ch in (1, 2, 4)}
             dram_gather64 = max([v for v in dram_gather64_by_chains.values() if v] or [0.0]) or None
+            # ... and of 128-byte records (one full L2 line per gather): two adjacent 64-byte records of the kernel (sibling nodes, the
+            # triangles of neighbouring leaves) share such a line, so no mix of its record fetches can bring in more bytes per second
+            dram_gather128 = max([v for v in (pr.gather128(24, steps=32, chains=1), pr.gather128(24, steps=16, chains=2)) if v] or [0.0]) or None
             flush4 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
             def step4():
@@ -716,14 +724,19 @@ def main():
             roof4["dram_gather32_peak_gbs"] = dram_gather * 32.0 if dram_gather else None
             roof4["dram_gather64_peak_gbs"] = dram_gather64 * 64.0 if dram_gather64 else None
             roof4["dram_gather64_gbs_by_chains_per_lane"] = {str(k): (v * 64.0 if v else None) for k, v in dram_gather64_by_chains.items()}
-            if roof4.get("hbm") and dram_gather64:
+            roof4["dram_gather128_peak_gbs"] = dram_gather128 * 128.0 if dram_gather128 else None
+            if roof4.get("hbm") and dram_gather64 and dram_gather128:
                 roof4["hbm"]["random64_peak"] = dram_gather64 * 64.0
                 roof4["hbm"]["frac_of_random64_peak"] = roof4["hbm"]["achieved"] / (dram_gather64 * 64.0)
+                roof4["hbm"]["random128_peak"] = dram_gather128 * 128.0
+                roof4["hbm"]["frac_of_random128_peak"] = roof4["hbm"]["achieved"] / (dram_gather128 * 128.0)
                 roof4["bound"] = "hbm"
                 roof4["l2_gather"] = {k: roof4[k] for k in ("achieved", "peak", "frac")}
-                roof4["achieved"], roof4["peak"], roof4["frac"] = roof4["hbm"]["achieved"], dram_gather64 * 64.0, roof4["hbm"]["frac_of_random64_peak"]
-                roof4["what"] = ("DRAM bytes per trace launch (ncu dram__bytes_read+write, committed capture) per second of kernel time (live CUDA events), against the rate of "
-                                 "dependent random 64-byte reads from a 2 GB DRAM-resident table measured by the in-process probe (best of 1, 2 and 4 independent chains per lane)")
+                roof4["achieved"], roof4["peak"], roof4["frac"] = roof4["hbm"]["achieved"], dram_gather128 * 128.0, roof4["hbm"]["frac_of_random128_peak"]
+                roof4["what"] = ("DRAM bytes per trace launch (ncu dram__bytes_read+write, committed capture) per second of kernel time (live CUDA events), against the rate at which "
+                                 "dependent random reads of whole 128-byte lines come out of a 2 GB DRAM-resident table (in-process probe, best of 1 and 2 chains per lane).  The kernel's "
+                                 "records are 64 bytes; two neighbours share a line, so its ceiling lies between the random-64-byte rate (hbm.random64_peak, which it exceeds: "
+                                 "hbm.frac_of_random64_peak) and this one")
             line["c4"] = {"workload": "synthetic %d-triangle lit box (seed %d), 1920x1080, 8 spp, depth 8, one GPU" % (len(sc4["triangles"]) // 48, args.scene_seed),
                           "fast_nodes": mat4.getInfo("fast_nodes"), "record_bytes": int(mat4.getInfo("fast_node_count")) * 64 + (len(sc4["triangles"]) // 48) * 64,
                           "value": c4.rays / 3 / (ms4 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms4, "roofline": roof4, "scene_build_s": gen4}

@@ -8,7 +8,7 @@ import numpy as np
 from oracleharness import AOV_DTYPE, RenderParams, Ubo, make_ubo
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "hostemu", "libvcrt_hostemu.so")
+SO = os.environ.get("VCRT_HOSTEMU_SO") or os.path.join(HERE, "hostemu", "libvcrt_hostemu.so")   # VCRT_HOSTEMU_SO: development A/B builds
 
 
 def have_hostemu():

@@ -147,6 +147,57 @@ extern "C" int vcrt_probe_gather64(int device, int records_log2, int steps, int 
     return 0;
 }
 
+// 128-byte records (one full L2 line, four sectors per gather): the most a random record fetch can bring in per DRAM transaction.
+// Two adjacent 64-byte records of the trace kernel (sibling nodes, neighbouring leaves' triangles) share such a line, so the
+// kernel's DRAM rate lies between the 64-byte and the 128-byte gather ceilings.
+template <int CHAINS>
+__global__ void __launch_bounds__(128) chase128_kernel(const Rec* __restrict__ rec, unsigned mask128, int steps, unsigned* out) {
+    unsigned ix[CHAINS], acc = 0u;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) ix[c] = mix32((blockIdx.x * blockDim.x + threadIdx.x) * CHAINS + c) & mask128;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            const Rec* p = rec + 4 * (size_t)ix[c];
+            const Rec a = ldg256(p), b = ldg256(p + 1), d = ldg256(p + 2), e = ldg256(p + 3);
+            acc ^= a.a[0] ^ a.a[7] ^ b.a[0] ^ b.a[3] ^ d.a[1] ^ d.a[6] ^ e.a[2] ^ e.a[5];
+            ix[c] = (a.a[4] ^ (b.a[4] >> 1) ^ (d.a[4] >> 2) ^ (e.a[4] >> 3) ^ (unsigned)c) & mask128;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+extern "C" int vcrt_probe_gather128(int device, int records_log2, int steps, int chains, int reps, double* g_per_s) {
+    if (!g_per_s || records_log2 < 4 || records_log2 > 26 || steps < 1 || (chains != 1 && chains != 2)) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t n = (size_t)1 << records_log2;
+    const int blocks = sms * 10 * 6, threads = 128;
+    Rec* d = nullptr; unsigned* out = nullptr;
+    if (cudaMalloc(&d, n * 4 * sizeof(Rec)) != cudaSuccess || cudaMalloc(&out, (size_t)blocks * threads * 4) != cudaSuccess) { cudaFree(d); return -3; }
+    fill_kernel<<<sms * 8, 256>>>(d, n * 4, 0xffffffffu);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep <= reps; ++rep) {
+        cudaEventRecord(e0);
+        if (chains == 2) chase128_kernel<2><<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
+        else chase128_kernel<1><<<blocks, threads>>>(d, (unsigned)(n - 1), steps, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d); cudaFree(out);
+    if (err != cudaSuccess) return -4;
+    *g_per_s = (double)blocks * threads * steps * chains / (best * 1e-3) / 1e9;
+    return 0;
+}
+
 extern "C" int vcrt_probe_stream(int device, size_t bytes, int passes, int reps, double* gb_per_s) {
     if (!gb_per_s || bytes < 4096 || passes < 1) return -1;
     if (cudaSetDevice(device) != cudaSuccess) return -2;
