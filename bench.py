@@ -384,13 +384,13 @@ def main():
     base = params_for(total_spp)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def step(p=base):
+    def step(p=base, mode=None):
         if group is None:
             mat.clearAccum()
             model.renderCommand(None, 0, p)
             mat.resolve(p.sample_count, 0.0)
         else:
-            group.render(model, p, args.sharding, 0.0)     # clear + this rank's share + ONE NCCL collective + resolve, all on `stream`
+            group.render(model, p, mode or args.sharding, 0.0)     # clear + this rank's share + ONE NCCL collective + resolve, all on `stream`
 
     def barrier():
         torch.cuda.synchronize()
@@ -398,9 +398,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(p, steps, warmup):
+    def timed_steps(p, steps, warmup, mode=None):
         for _ in range(warmup):
-            step(p)
+            step(p, mode)
         barrier()
         mat.resetCounters()
         evs = []
@@ -410,7 +410,7 @@ def main():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            step(p)
+            step(p, mode)
             e1.record(stream)
             evs.append((e0, e1))
         barrier()
@@ -465,7 +465,15 @@ def main():
     strong = None
     if world > 1 and args.scaling == "weak" and not args.no_strong:
         ps = params_for(args.spp)
-        _, tot_s, ms_s = timed_steps(ps, args.steps, 2)
+        # both partitions of the frame: sample slices (every GPU all pixels, spp / N samples; f32 sums reduced onto rank 0) and 32x32
+        # tiles (every GPU all samples of its tiles -- bounce 0 traced for 1/N of the pixels only; packed rgba8 tiles all-gathered,
+        # bit-identical to one GPU); the headline of the record is the faster one
+        runs = {}
+        for mode_ in ("samples", "tiles"):
+            _, tot_m, ms_m = timed_steps(ps, args.steps, 2, mode_)
+            runs[mode_] = (tot_m, ms_m)
+        best_mode = min(runs, key=lambda k: runs[k][1])
+        tot_s, ms_s = runs[best_mode]
         one_ms = 0.0
         if rank == 0:
             def one():
@@ -482,10 +490,13 @@ def main():
             torch.cuda.synchronize()
             one_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
         barrier()
-        strong = {"what": "the %d-spp frame of the N=1 workload split over %d GPUs (%s), collective and resolve inside the timed region" % (args.spp, world, args.sharding),
+        strong = {"what": "the %d-spp frame of the N=1 workload split over %d GPUs (%s), collective and resolve inside the timed region" % (args.spp, world, best_mode),
+                  "sharding": best_mode,
                   "ms_per_step": ms_s / args.steps, "value": tot_s[0] / (ms_s * 1e-3) / 1e6, "unit": "Mrays/s", "spp_total": args.spp, "steps": args.steps,
                   "n1_ms_per_step_same_run": one_ms, "speedup_vs_n1_same_run": one_ms / (ms_s / args.steps) if ms_s > 0 else None,
-                  "efficiency_vs_n1_same_run": one_ms / (ms_s / args.steps) / world if ms_s > 0 else None}
+                  "efficiency_vs_n1_same_run": one_ms / (ms_s / args.steps) / world if ms_s > 0 else None,
+                  "by_sharding": {k: {"ms_per_step": v[1] / args.steps, "value": v[0][0] / (v[1] * 1e-3) / 1e6,
+                                      "efficiency_vs_n1_same_run": one_ms / (v[1] / args.steps) / world if v[1] > 0 else None} for k, v in runs.items()}}
 
     # ---- e2e: through the public API with host buffers, host<->device copies inside the timed region.
     # Headline protocol = the reference's own frame loop (main.cpp:166-183, :228, :323-395), which is also what the reference

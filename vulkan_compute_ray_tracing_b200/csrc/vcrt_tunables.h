@@ -37,6 +37,15 @@
 #define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
 #endif
 
+#ifndef VCRT_TAIL_SPLIT
+#define VCRT_TAIL_SPLIT 1  /* trace kernel: once the queue is dry, idle lanes of a warp take subtrees off the stacks of its busy lanes (vcrt_wavefront.cuh) */
+#endif
+#ifndef VCRT_TAIL_ROUNDS
+#define VCRT_TAIL_ROUNDS 2  /* ... visit / leaf rounds between two rounds of reports and donations */
+#endif
+#ifndef VCRT_TAIL_PASSES
+#define VCRT_TAIL_PASSES 1  /* ... donation passes per round of donations (a donor gives one subtree per pass) */
+#endif
 /* r02 experiments that did not make it (logs under profiles/, code under tools/experiments/):
  *   cache policy of the triangle-record loads (L2 evict-first / no hint / L1 no-allocate instead of L2 evict-last): +-1 % on C3 and on the
  *     10 M-triangle scene, L1 no-allocate -3 % (r02_v12_ab_tri_policy.log);

@@ -143,7 +143,11 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                 idx = 0xffffffffu;
             }
         }
+#if VCRT_TAIL_SPLIT
+        if (__any_sync(FULL, done)) break;   // the queue has run dry: the rays still in flight are finished by the tail loop below
+#else
         if (__all_sync(FULL, done)) break;
+#endif
 
         for (;;) {
             // ---- VCRT_VISITS inner-node visits for every lane that has one; a lane that arrives at a leaf postpones it
@@ -208,6 +212,130 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             break;   // enough lanes want a new ray (nf >= refill_t), or nothing but finished lanes is left
         }
     }
+#if VCRT_TAIL_SPLIT
+    // ---- tail: the queue is dry, every lane either still walks its last ray or idles.  A launch ends when its LONGEST ray ends, and
+    // a ray that needs a few hundred visits is walked by one lane, one dependent round trip after the other, while the rest of
+    // the GPU waits (~110 us per launch on C3: 2 % of a 64-spp step, 15 % of an 8-spp one, most of a 1-spp frame).  Here the idle
+    // lanes of a warp take subtrees off the stacks of its busy lanes: a donor hands over the top of its stack (an inner node it has
+    // not entered yet) together with its ray and its current closest hit; the helper walks that subtree with the donor's
+    // arithmetic, and its result is merged into the donor's by the traversal's own rule (smaller t, then smaller slot), so the
+    // record that is finally stored is the one a single lane would have found.  Helpers donate in turn; a lane's result is final
+    // once its own walk is over and every helper it handed work to has reported back (`out`).
+    {
+        __shared__ uint32_t s_owner[VCRT_PBLOCK];
+        const unsigned lane = threadIdx.x & 31u;
+        const uint32_t wbase = threadIdx.x & ~31u;
+        bool helper = false;
+        uint32_t out = 0u;   // helpers that have not reported back yet
+        for (;;) {
+            bool working = t.node != EMPTY || pending != EMPTY;
+            // (1) a lane whose own ray is finished for good stores it
+            if (idx != 0xffffffffu && !working && out == 0u) {
+                stream_st(w.hit + idx, make_uint2(f2u(t.closest), (uint32_t)t.best));
+                idx = 0xffffffffu;
+            }
+            // (2) helpers that are through report to their owners
+            unsigned fh = __ballot_sync(FULL, helper && !working && out == 0u);
+            while (fh) {
+                const int h = __ffs(fh) - 1;
+                fh &= fh - 1u;
+                const int o = (int)s_owner[wbase + (uint32_t)h];
+                const float hc = __shfl_sync(FULL, t.closest, h);
+                const int32_t hb = __shfl_sync(FULL, t.best, h);
+                if ((int)lane == o) {
+                    if (hb >= 0 && (hc < t.closest || (hc == t.closest && hb < t.best))) { t.closest = hc; t.best = hb; }
+                    out--;
+                }
+                if ((int)lane == h) helper = false;
+            }
+            // (3) idle lanes take the top-of-stack subtree of busy lanes
+            const unsigned idle = __ballot_sync(FULL, idx == 0xffffffffu && !helper && !working);
+            const unsigned donors = __ballot_sync(FULL, working && tos >= 0);
+            if (!__any_sync(FULL, working || idx != 0xffffffffu || helper)) break;   // nobody holds a ray or works for one
+#pragma unroll 1
+            for (int pass = 0; pass < VCRT_TAIL_PASSES; ++pass) {
+            const unsigned idle_now = pass == 0 ? idle : __ballot_sync(FULL, idx == 0xffffffffu && !helper && t.node == EMPTY && pending == EMPTY);
+            const unsigned donors_now = pass == 0 ? donors : __ballot_sync(FULL, (t.node != EMPTY || pending != EMPTY) && tos >= 0);
+            const int n = min(__popc(idle_now), __popc(donors_now));
+            if (n == 0) break;
+            {
+                const unsigned below = (1u << lane) - 1u;
+                const int ri = __popc(idle_now & below), rd = __popc(donors_now & below);
+                const bool recv = ((idle_now >> lane) & 1u) && ri < n, give = ((donors_now >> lane) & 1u) && rd < n;
+                const int src = recv ? (int)__fns(donors_now, 0u, ri + 1) : (int)lane;
+                const int32_t in_node = __shfl_sync(FULL, tos, src);
+                const float in_c = __shfl_sync(FULL, t.closest, src);
+                const int32_t in_b = __shfl_sync(FULL, t.best, src);
+                const float ix = __shfl_sync(FULL, t.idir.x, src), iy = __shfl_sync(FULL, t.idir.y, src), iz = __shfl_sync(FULL, t.idir.z, src);
+                const float ox = __shfl_sync(FULL, t.ood.x, src), oy = __shfl_sync(FULL, t.ood.y, src), oz = __shfl_sync(FULL, t.ood.z, src);
+                const uint32_t sx = __shfl_sync(FULL, t.selx, src), sy = __shfl_sync(FULL, t.sely, src), sz = __shfl_sync(FULL, t.selz, src);
+                if (give) {   // the donor's next stack entry becomes its top; it now waits for one more report
+                    t.sp -= 1;
+                    sr.load_if(true, t.sp, tos);
+                    out++;
+                }
+                if (recv) {
+                    t.node = in_node; t.closest = in_c; t.best = in_b;
+                    t.idir = f3(ix, iy, iz); t.ood = f3(ox, oy, oz);
+                    t.selx = sx; t.sely = sy; t.selz = sz;
+                    t.sp = 1; tos = EMPTY; pending = EMPTY;
+                    helper = true;
+                    s_owner[threadIdx.x] = (uint32_t)src;
+#if VCRT_SMEMRAY
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s_ray[k][threadIdx.x] = s_ray[k][wbase + (uint32_t)src];
+#endif
+                }
+#if !VCRT_SMEMRAY
+                cur.o = f3(__shfl_sync(FULL, cur.o.x, src), __shfl_sync(FULL, cur.o.y, src), __shfl_sync(FULL, cur.o.z, src));
+                cur.d = f3(__shfl_sync(FULL, cur.d.x, src), __shfl_sync(FULL, cur.d.y, src), __shfl_sync(FULL, cur.d.z, src));
+#endif
+                __syncwarp();
+            }
+            }
+            // (4) a few rounds of: visit, postpone, test -- no votes: with a few lanes left what counts is each lane's own latency
+#pragma unroll 1
+            for (int round = 0; round < VCRT_TAIL_ROUNDS; ++round) {
+                if (t.node >= 0) {
+                    if (COUNT) st.nodes++;
+                    if (QN == 2) {
+                        const Words8* p = s.q4nodes + 2 * (size_t)t.node;
+                        const Words8 na = ldg8(p), nb = ldg8(p + 1);
+                        int32_t c[4];
+                        trav_test4(t, na, nb, c);
+                        trav_descend4(t, s, c, pending, tos, sr);
+                    } else {
+                        float lN, rN;
+                        bool hl, hr;
+                        int32_t cl, cr;
+                        trav_test_children<QN>(t, s, lN, rN, hl, hr, cl, cr);
+                        trav_descend(t, lN, rN, hl, hr, cl, cr, pending, tos, sr);
+                    }
+                }
+                {
+                    const bool park = (uint32_t)t.node > 0x80000000u && pending == EMPTY;
+                    pending = park ? t.node : pending;
+                    trav_pop_if(park, t, tos, sr);
+                }
+                if (pending != EMPTY) {
+                    if (COUNT) st.tris++;
+#if VCRT_SMEMRAY
+                    Ray lr;
+                    lr.o = f3(s_ray[0][threadIdx.x], s_ray[1][threadIdx.x], s_ray[2][threadIdx.x]);
+                    lr.d = f3(s_ray[3][threadIdx.x], s_ray[4][threadIdx.x], s_ray[5][threadIdx.x]);
+                    trav_leaf_test(t, s, lr, pending);
+#else
+                    trav_leaf_test(t, s, cur, pending);
+#endif
+                    pending = EMPTY;
+                    const bool park = (uint32_t)t.node > 0x80000000u;
+                    pending = park ? t.node : pending;
+                    trav_pop_if(park, t, tos, sr);
+                }
+            }
+        }
+    }
+#endif
     // st.rays is non-zero only for PRIMARY (queued rays are counted once per launch above): every traced pixel answers the
     // bounce-0 closest-hit query of all its samples
     flush_stats(a, st, PRIMARY ? a.sample_count : 1u, PRIMARY);
