@@ -34,7 +34,7 @@ model = vcrt.ComputeModel(m)
 L = _native.lib()
 out = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
 for nb, name, flags, opts in [(int(nb), n_, f_, o_) for nb in a.bounces.split(",") for n_, f_, o_ in (
-        ("wavefront", 0, {}), ("wavefront no trace timing", 0, {"trace_timing": "off"}), ("megakernel", 16, {}), ("one thread per pixel", 8, {}))]:
+        ("auto", 0, {}), ("wavefront", 32, {}), ("wavefront no trace timing", 32, {"trace_timing": "off"}), ("megakernel", 16, {}), ("one thread per pixel", 8, {}))]:
     for k, v in {"trace_timing": "on", "wf_streams": "auto", **opts}.items():
         m.setOption(k, v)
     p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=nb, sample_count=1, flags=flags)

@@ -449,12 +449,12 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     // utilisation: 1.82 vs 2.09 ms per 1080p frame on C3, 0.84 vs 1.10 ms on the bundled scene (profiles/r02_v6_latency_*.log).
     bool one_launch = (p.flags & (VCRT_FLAG_STATIC_KERNEL | VCRT_FLAG_MEGAKERNEL)) != 0;
     // With two or more frames in flight (vcrt_frame_submit) the tails overlap the next frames' work anyway, and what counts is the
-    // work per frame: on a large scene the wavefront pipeline needs half the megakernel's (C3, depth 8, 1080p: 1.40 / 1.25 / 1.18 ms per
-    // frame with 2 / 3 / 4 frames in flight against the megakernel's 1.57 / 1.47 / 1.47; on the bundled 2 K-triangle scene the
-    // megakernel's single launch stays ahead: 0.72 / 0.60 / 0.60 against 0.76 / 0.68 / 0.64 -- profiles/r02_v11_latency_*.log).
+    // work per frame, where the wavefront pipeline is ahead: C3, depth 8, 1080p: 1.26 / 1.13 / 1.07 ms per frame with 2 / 3 / 4 frames in
+    // flight against the megakernel's 1.57 / 1.47 / 1.47; bundled scene 0.71 / 0.61 / 0.57 against 0.72 / 0.60 / 0.60
+    // (profiles/r02_v27_latency_*.log).
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && !(p.flags & VCRT_FLAG_WAVEFRONT) && a.sample_count == 1u) {
         const bool deep = a.env.max_bounces > 4u;
-        if (!(deep && fs && c->frames_n >= 2 && s.ntris >= 65536u)) {
+        if (!(deep && fs && c->frames_n >= 2)) {
             a.flags |= deep ? VCRT_FLAG_MEGAKERNEL : VCRT_FLAG_STATIC_KERNEL;
             one_launch = true;
         }

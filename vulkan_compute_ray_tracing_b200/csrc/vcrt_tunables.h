@@ -40,8 +40,11 @@
 #ifndef VCRT_TAIL_SPLIT
 #define VCRT_TAIL_SPLIT 1  /* trace kernel: once the queue is dry, idle lanes of a warp take subtrees off the stacks of its busy lanes (vcrt_wavefront.cuh) */
 #endif
+#ifndef VCRT_TAIL_PREFETCH
+#define VCRT_TAIL_PREFETCH 0  /* ... the records of the children a ray enters are prefetched into L1 (tail loop only): slower even there -- C3 at 1 / 8 spp 2567 -> 2228, 5631 -> 5326 Mrays/s, the 10 M-triangle scene 4374 -> 4178 (profiles/r02_v28_ab_tail_prefetch.log) */
+#endif
 #ifndef VCRT_TAIL_ROUNDS
-#define VCRT_TAIL_ROUNDS 2  /* ... visit / leaf rounds between two rounds of reports and donations */
+#define VCRT_TAIL_ROUNDS 2  /* ... visit / leaf rounds between two rounds of reports and donations (1 / 2 / 4 rounds x 1 / 2 / 4 passes: all within 3 %, profiles/r02_v26_ab_tail_split_tuning.log) */
 #endif
 #ifndef VCRT_TAIL_PASSES
 #define VCRT_TAIL_PASSES 1  /* ... donation passes per round of donations (a donor gives one subtree per pass) */

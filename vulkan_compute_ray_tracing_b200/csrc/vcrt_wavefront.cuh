@@ -303,6 +303,18 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                         const Words8 na = ldg8(p), nb = ldg8(p + 1);
                         int32_t c[4];
                         trav_test4(t, na, nb, c);
+#if VCRT_TAIL_PREFETCH
+                        // In the tail a lane's speed is the latency of its dependent round trips (an L2 hit per visit and per triangle
+                        // test), and the L1TEX pipe that a divergent prefetch costs in the main loop is idle: the records of every child
+                        // the ray enters are pulled into L1 now, one visit's arithmetic ahead of their use (or several, for the stack).
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (c[i] != EMPTY) {
+                                const char* rec = c[i] >= 0 ? (const char*)(s.q4nodes + 2 * (size_t)c[i]) : (const char*)(s.ftris + 4 * (size_t)(~c[i]));
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 32));
+                            }
+#endif
                         trav_descend4(t, s, c, pending, tos, sr);
                     } else {
                         float lN, rN;
