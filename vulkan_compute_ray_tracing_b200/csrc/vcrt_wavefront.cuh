@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             const int n = min(__popc(idle_now), __popc(donors_now));
             if (n == 0) break;
             {
+                __syncwarp();   // the donors' rays in shared memory were written by other lanes of this warp
                 const unsigned below = (1u << lane) - 1u;
                 const int ri = __popc(idle_now & below), rd = __popc(donors_now & below);
                 const bool recv = ((idle_now >> lane) & 1u) && ri < n, give = ((donors_now >> lane) & 1u) && rd < n;
