@@ -121,10 +121,6 @@ cudaError_t VCRT_TU_NAME(const KernelArgs& a, int shader, int rng, int trig, boo
 
 #if VCRT_TU_TRAV == 1
 // ---------------------------------------------------------------------------------------------- wavefront pipeline
-__global__ void wf_reset_kernel(unsigned int* counts, int which) {
-    counts[which] = 0u;   // the queue about to be filled
-    counts[2] = 0u;       // the trace fetch counter
-}
 
 template <int SHADER, int RNG_MODE, int TRIG>
 static cudaError_t wf_run(const KernelArgs& a, bool count, const WfPipes& pipes, uint32_t* launches, TraceTimer* timer) {
@@ -163,10 +159,12 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, const WfPipes& pipes,
         b.nitems = items - item0 < per_batch ? items - item0 : per_batch;
         b.npaths = b.nitems * a.sample_count;
         b.cur = 0u; b.bounce = 0u;
+        // queue sizes and the trace kernel's fetch counter start at zero; from here on the trace kernel clears the queue its shade
+        // kernel fills and the shade kernel clears the fetch counter: one memset per batch instead of a reset launch per bounce
+        if ((e = cudaMemsetAsync(w.counts, 0, 3 * sizeof(unsigned int), stream)) != cudaSuccess) return e;
         for (uint32_t bounce = 0; bounce < a.env.max_bounces; ++bounce) {
             b.bounce = bounce;
             const int pi = bounce == 0u ? 1 : 0;   // bounce 0 reads no queue: one primary ray per pixel, generated from the item id
-            wf_reset_kernel<<<1, 1, 0, stream>>>(w.counts, (int)(b.cur ^ 1u));
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (timer && (e = timer->begin(stream, &t0, &t1)) != cudaSuccess) return e;
             const uint32_t rays_max = pi ? b.nitems : b.npaths;   // no more blocks than there can be rays (small frames)
@@ -175,7 +173,7 @@ static cudaError_t wf_run(const KernelArgs& a, bool count, const WfPipes& pipes,
             if (timer && (e = timer->end(stream, t0, t1, pi != 0)) != cudaSuccess) return e;
             if (pi) wf_shade_kernel<SHADER, RNG_MODE, TRIG, true><<<shade_grid, 256, 0, stream>>>(a, w, b);
             else wf_shade_kernel<SHADER, RNG_MODE, TRIG, false><<<shade_grid, 256, 0, stream>>>(a, w, b);
-            *launches += 3;
+            *launches += 2;
             b.cur ^= 1u;
         }
         if (pipes.before_accumulate && bi == 0 && (e = cudaStreamWaitEvent(stream, pipes.before_accumulate, 0)) != cudaSuccess) return e;   // frames in flight: fold in frame order

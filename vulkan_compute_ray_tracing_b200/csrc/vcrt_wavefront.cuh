@@ -349,6 +349,9 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
         }
     }
 #endif
+    // the queue the shade kernel behind this launch appends to starts empty (this kernel does not touch it; the fetch counter this
+    // kernel uses is cleared by the shade kernel in turn: no separate reset launch per bounce)
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[b.cur ^ 1u] = 0u;
     // st.rays is non-zero only for PRIMARY (queued rays are counted once per launch above): every traced pixel answers the
     // bounce-0 closest-hit query of all its samples
     flush_stats(a, st, PRIMARY ? a.sample_count : 1u, PRIMARY);
@@ -361,9 +364,12 @@ __global__ void __launch_bounds__(256, VCRT_SHADE_MINB) wf_shade_kernel(const __
     const uint32_t count = PRIMARY ? b.npaths : w.counts[b.cur];
     const float4* __restrict__ rays = w.q[b.cur];
     float4* __restrict__ next = w.q[b.cur ^ 1u];
-    if (!PRIMARY && blockIdx.x == 0 && threadIdx.x == 0 && count) {   // the rays the preceding trace launch walked: one query = one traversal each
-        atomicAdd(a.counters + 0, (unsigned long long)count);
-        atomicAdd(a.counters + 4, (unsigned long long)count);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        w.counts[2] = 0u;   // the trace kernel's fetch counter, for the next bounce (the trace launch that used it is over)
+        if (!PRIMARY && count) {   // the rays the preceding trace launch walked: one query = one traversal each
+            atomicAdd(a.counters + 0, (unsigned long long)count);
+            atomicAdd(a.counters + 4, (unsigned long long)count);
+        }
     }
     for (uint32_t base = blockIdx.x * 256u; base < count; base += gridDim.x * 256u) {   // base is warp-uniform
         const uint32_t i = base + threadIdx.x;
