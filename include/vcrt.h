@@ -183,7 +183,7 @@ int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile
  * literal hit_bvh), "fast"; "wf_batch_paths":
  *  paths per wavefront batch (queue memory: 120 B per path); "wf_streams": "auto" (default, = 1) or 1..4 -- the render is cut
  * into that many batches, run as parallel pipelines on separate streams with their own queue sets (an A/B knob: measured
- * slower than one pipeline on a 1-spp frame); "trace_timing": "on" (default) | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
+ * slower than one pipeline on a 1-spp frame); "trace_timing": "auto" (default: multi-sample renders only) | "on" | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
  * "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 

@@ -1022,3 +1022,30 @@ def test_frames_in_flight_render_params(doge, family, accum):
     for b in bufs:
         b.free()
     g.close()
+
+
+@pytest.mark.parametrize("fmt", ["q15x4", "q15", "f32"])
+def test_tail_loop_work_sharing(oracle, fmt):
+    """The trace kernel's tail loop (idle lanes of a warp walk subtrees handed over by its busy lanes, results merged by the
+    traversal's own rule): launches with fewer rays than lanes on a random-triangle soup -- long rays, deep stacks, plenty of
+    equal-t candidates among the 200 duplicated triangles -- run almost entirely in it.  Every node format, against the oracle and
+    against the kernels that have no such loop: bit-identical f32 accumulation and primary hits."""
+    from gpuharness import GpuScene
+    import tinybvh
+    sc = dict(small_scene(n_tris=20000, seed=11))
+    tris = sc["triangles"].reshape(-1, 48)
+    t2 = np.concatenate([tris, tris[:200]]).reshape(-1).copy()      # 200 triangles twice: the tie rule must pick the same copy whichever lane finds which
+    sc["triangles"] = t2
+    sc["bvh"] = tinybvh.build_bvh(t2.view(tinybvh.TRI), seed=4, tie_seed=6).view(np.uint8).reshape(-1).copy()
+    cam = (0.0, 6.0, 1.5)
+    w, h = 96, 64
+    kw = dict(shader="full", max_bounces=8, sample_count=3, accum="f32", rng="philox", trig="portable", philox_seed=5, stack_depth=64)
+    a = oracle.render(sc, cam, w, h, make_params(**kw), want_aov=True)
+    g = GpuScene(sc, w, h)
+    g.material.setOption("fast_nodes", fmt)
+    b = g.render(cam, traversal="fast", flags=32, want_aov=True, **kw)      # wavefront pipeline (tail loop)
+    assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), fmt
+    for flags in (8, 16):                                                     # one thread per pixel, megakernel
+        c = g.render(cam, traversal="fast", flags=flags, want_aov=True, **kw)
+        assert same_bits(b["accumf"], c["accumf"]) and same_bits(b["aov"], c["aov"]), (fmt, flags)
+    g.close()

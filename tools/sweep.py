@@ -31,6 +31,8 @@ m.addStorageImage(vcrt.Image(w, h)); m.addStorageImage(vcrt.Image(w, h))
 for n in ("triangles", "materials", "bvh", "lights", "spheres"):
     m.addStorageBufferBundle(vcrt.BufferUtils.createBundle(vcrt.BufferBundle(1), scene[n]))
 model = vcrt.ComputeModel(m)
+if a.trace:
+    m.setOption("trace_timing", "on")   # "auto" leaves 1-spp renders untimed
 keys = [o.split("=")[0] for o in a.opts]
 vals = [o.split("=")[1].split(",") for o in a.opts]
 p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=a.bounces, sample_count=a.spp,

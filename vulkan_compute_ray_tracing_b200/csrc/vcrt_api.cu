@@ -132,9 +132,9 @@ int vcrt_set_option(vcrt_ctx* c, const char* key, const char* value) {
         c->wf_streams = n;
         return VCRT_OK;
     }
-    if (k == "trace_timing") {
-        if (v != "on" && v != "off") return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: trace_timing must be 'on' or 'off'");
-        c->trace_timer.enabled = v == "on";
+    if (k == "trace_timing") {   // "auto": around the trace launches of multi-sample renders only (a 1-spp frame has 16 such events: 2 % of its time)
+        if (v != "on" && v != "off" && v != "auto") return fail(c, VCRT_ERR_INVALID, "vcrt_set_option: trace_timing must be 'auto', 'on' or 'off'");
+        c->trace_timing = v == "auto" ? 0 : v == "on" ? 1 : 2;
         return VCRT_OK;
     }
     if (k == "leaf_threshold" || k == "shade_threshold" || k == "continue_threshold") {
@@ -512,6 +512,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
         if (!fs && sets > 1 && !c->fork_ev && (e = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming)) != cudaSuccess) { give_back(); return cuda_fail(c, e, "create event"); }
         pipes.fork = c->fork_ev;
         nlaunch = 0;
+        c->trace_timer.enabled = c->trace_timing == 1 || (c->trace_timing == 0 && a.sample_count > 1u);
         e = launch_render_wavefront(a, (int)p.shader, (int)p.rng_mode, (int)p.trig_mode, count, pipes, &nlaunch, &c->trace_timer);
     } else {
         if (fs) a.sample_out = (float4*)fs->sample.ptr;   // one launch: the sample is handed to the fold kernel

@@ -81,6 +81,7 @@ struct vcrt_ctx {
     double kernel_ms = 0.0;
     uint64_t launches = 0;
     vcrt::TraceTimer trace_timer;
+    int trace_timing = 0;                 // option "trace_timing": 0 "auto" (multi-sample renders only) | 1 "on" | 2 "off"
     double trace_ms = 0.0;
     uint64_t trace_launches = 0;
 };
