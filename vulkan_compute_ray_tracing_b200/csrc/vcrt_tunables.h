@@ -49,6 +49,8 @@
 #ifndef VCRT_TAIL_PASSES
 #define VCRT_TAIL_PASSES 1  /* ... donation passes per round of donations (a donor gives one subtree per pass) */
 #endif
+/* tail loop, also tried: the loads of a lane's node and of its postponed triangle issued together (one round trip per round instead of two): ~100 bytes of
+ * spills in the tail loop, C3 at 1 / 2 / 8 spp 2597 -> 2312, 3796 -> 3477, 5652 -> 5436 Mrays/s (profiles/r02_v33_ab_tail_combined_loads.log) */
 /* r02 experiments that did not make it (logs under profiles/, code under tools/experiments/):
  *   cache policy of the triangle-record loads (L2 evict-first / no hint / L1 no-allocate instead of L2 evict-last): +-1 % on C3 and on the
  *     10 M-triangle scene, L1 no-allocate -3 % (r02_v12_ab_tri_policy.log);
