@@ -40,6 +40,9 @@
 #ifndef VCRT_TAIL_SPLIT
 #define VCRT_TAIL_SPLIT 1  /* trace kernel: once the queue is dry, idle lanes of a warp take subtrees off the stacks of its busy lanes (vcrt_wavefront.cuh) */
 #endif
+#ifndef VCRT_TAIL_EXCHANGE
+#define VCRT_TAIL_EXCHANGE 0  /* ... owners and helpers exchange their closest hits at every round of reports, not only at the end: the loop over all helpers costs more than the culling returns -- C3 at 1 / 2 / 8 spp 2584 -> 2444, 3764 -> 3600, 5611 -> 5525 Mrays/s (profiles/r02_v37_ab_tail_exchange.log) */
+#endif
 #ifndef VCRT_TAIL_PREFETCH
 #define VCRT_TAIL_PREFETCH 0  /* ... the records of the children a ray enters are prefetched into L1 (tail loop only): slower even there -- C3 at 1 / 8 spp 2567 -> 2228, 5631 -> 5326 Mrays/s, the 10 M-triangle scene 4374 -> 4178 (profiles/r02_v28_ab_tail_prefetch.log) */
 #endif

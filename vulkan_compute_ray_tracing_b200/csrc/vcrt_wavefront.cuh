@@ -234,20 +234,38 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
                 stream_st(w.hit + idx, make_uint2(f2u(t.closest), (uint32_t)t.best));
                 idx = 0xffffffffu;
             }
-            // (2) helpers that are through report to their owners
+            // (2) helpers report to their owners: those that are through for good (the owner then waits for one helper less), and --
+            //     VCRT_TAIL_EXCHANGE -- all the others too, so that an owner culls with what its helpers have found so far and, the other
+            //     way round, a helper with what its owner knows by now
+#if VCRT_TAIL_EXCHANGE
+            const unsigned fin = __ballot_sync(FULL, helper && !working && out == 0u);
+            unsigned fh = __ballot_sync(FULL, helper);
+#else
             unsigned fh = __ballot_sync(FULL, helper && !working && out == 0u);
+            const unsigned fin = fh;
+#endif
+            const bool any_helper = fh != 0u;
             while (fh) {
                 const int h = __ffs(fh) - 1;
                 fh &= fh - 1u;
                 const int o = (int)s_owner[wbase + (uint32_t)h];
                 const float hc = __shfl_sync(FULL, t.closest, h);
                 const int32_t hb = __shfl_sync(FULL, t.best, h);
+                const bool done_h = ((fin >> h) & 1u) != 0u;
                 if ((int)lane == o) {
                     if (hb >= 0 && (hc < t.closest || (hc == t.closest && hb < t.best))) { t.closest = hc; t.best = hb; }
-                    out--;
+                    if (done_h) out--;
                 }
-                if ((int)lane == h) helper = false;
+                if ((int)lane == h && done_h) helper = false;
             }
+#if VCRT_TAIL_EXCHANGE
+            if (any_helper) {
+                const int o = helper ? (int)s_owner[threadIdx.x] : (int)lane;
+                const float oc = __shfl_sync(FULL, t.closest, o);
+                const int32_t ob = __shfl_sync(FULL, t.best, o);
+                if (helper && ob >= 0 && (oc < t.closest || (oc == t.closest && ob < t.best))) { t.closest = oc; t.best = ob; }
+            }
+#endif
             // (3) idle lanes take the top-of-stack subtree of busy lanes
             const unsigned idle = __ballot_sync(FULL, idx == 0xffffffffu && !helper && !working);
             const unsigned donors = __ballot_sync(FULL, working && tos >= 0);
