@@ -34,8 +34,8 @@ model = vcrt.ComputeModel(m)
 L = _native.lib()
 out = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
 for nb, name, flags, opts in [(int(nb), n_, f_, o_) for nb in a.bounces.split(",") for n_, f_, o_ in (
-        ("auto", 0, {}), ("wavefront", 32, {}), ("wavefront no trace timing", 32, {"trace_timing": "off"}), ("megakernel", 16, {}), ("one thread per pixel", 8, {}))]:
-    for k, v in {"trace_timing": "on", "wf_streams": "auto", **opts}.items():
+        ("auto", 0, {}), ("wavefront", 32, {}), ("wavefront with trace timing", 32, {"trace_timing": "on"}), ("megakernel", 16, {}), ("one thread per pixel", 8, {}))]:
+    for k, v in {"trace_timing": "auto", "wf_streams": "auto", **opts}.items():
         m.setOption(k, v)
     p = vcrt.render_params(shader="full", traversal="fast", rng="philox", accum="f32", max_bounces=nb, sample_count=1, flags=flags)
     name = "depth %d %s" % (nb, name)
@@ -58,6 +58,7 @@ for nb, name, flags, opts in [(int(nb), n_, f_, o_) for nb in a.bounces.split(",
     print("%-36s %.3f ms/frame  %.0f Mrays/s  (%d launches/frame, kernels %.3f ms/frame)" % (name, 1e3 * dt / a.frames, c.rays / dt / 1e6, c.launches / a.frames, c.kernel_ms / a.frames), flush=True)
 
 
+m.setOption("trace_timing", "auto")
 # ---- the pipelined loop (vcrt_frames_begin / vcrt_frame_submit / vcrt_frame_wait: the reference's MAX_FRAMES_IN_FLIGHT, main.cpp:68)
 for nb in [int(x) for x in a.bounces.split(",")]:
     for name, flags in (("wavefront", 32), ("megakernel", 16), ("one thread per pixel", 8)):
