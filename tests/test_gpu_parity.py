@@ -1049,3 +1049,49 @@ def test_tail_loop_work_sharing(oracle, fmt):
         c = g.render(cam, traversal="fast", flags=flags, want_aov=True, **kw)
         assert same_bits(b["accumf"], c["accumf"]) and same_bits(b["aov"], c["aov"]), (fmt, flags)
     g.close()
+
+
+@pytest.mark.parametrize("family", ["static", "wavefront"])
+def test_frames_in_flight_tile_shard_and_coverage(doge, family):
+    """Frames in flight that cover only part of the image -- a tile shard (tile_rank / tile_count) and the reference's dispatch
+    coverage (floor(W/32) x floor(H/32) groups, main.cpp:228): the fold touches the covered pixels only, the rest of the target and of
+    the accumulation stay as the synchronous calls leave them."""
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from gpuharness import GpuScene
+    w, h, n = 200, 136, 4
+    flags = {"static": vcrt.FLAG_STATIC_KERNEL, "wavefront": vcrt.FLAG_WAVEFRONT}[family] | vcrt.FLAG_REF_DISPATCH_COVERAGE
+    kw = dict(shader="full", traversal="fast", rng="philox", accum="f32", trig="libm", max_bounces=3, sample_count=1, philox_seed=3, flags=flags,
+              tile_rank=1, tile_count=3)
+    frames = {}
+    for mode in ("sync", "in_flight"):
+        g = GpuScene(doge, w, h)
+        g.set_camera(CAM, 0)
+        g.material.clearAccum()
+        out = []
+        if mode == "sync":
+            for k in range(n):
+                g.model.renderCommand(None, 0, vcrt.render_params(**kw, sample_begin=k))
+                g.material.resolve(k + 1, 0.0)
+                out.append(g.target.read())
+        else:
+            bufs = [vcrt.PinnedFrame(w, h) for _ in range(2)]
+            g.material.framesBegin(2)
+            for k in range(n):
+                g.material.frameWait(k % 2)
+                if k >= 2:
+                    out.append(bufs[k % 2].array.copy())
+                g.material.frameSubmit(vcrt.render_params(**kw, sample_begin=k), total_samples=k + 1, out=bufs[k % 2])
+            for k in range(n, n + 2):
+                g.material.frameWait(k % 2)
+                out.append(bufs[k % 2].array.copy())
+            g.material.framesEnd()
+            for b in bufs:
+                b.free()
+        frames[mode] = (out, g.material.readAccumF32(), g.target.read())
+        g.close()
+    assert len(frames["sync"][0]) == len(frames["in_flight"][0]) == n
+    for k in range(n):
+        assert same_bits(frames["sync"][0][k], frames["in_flight"][0][k]), (family, k)
+    assert same_bits(frames["sync"][1], frames["in_flight"][1]) and same_bits(frames["sync"][2], frames["in_flight"][2])
+    covered = frames["sync"][1][..., 3] > 0
+    assert 0 < covered.sum() < w * h / 2      # a third of the tiles, minus the uncovered border
