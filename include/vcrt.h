@@ -69,7 +69,7 @@ enum { VCRT_FLAG_REF_DISPATCH_COVERAGE = 1u, /* only floor(W/32)*32 x floor(H/32
        VCRT_FLAG_MEGAKERNEL = 16u,           /* fast traversal in the persistent-warps megakernel (whole paths per lane, no barrier between bounces) */
        VCRT_FLAG_WAVEFRONT = 32u             /* fast traversal in the wavefront pipeline whatever the shape of the call */
        /* none of the three: by the shape of the call -- 1 spp and depth <= 4: one launch, one thread per pixel; 1 spp and deeper: the megakernel on
-          scenes below 64 Ki triangles when one frame is rendered at a time, else the wavefront pipeline; more samples: the wavefront pipeline */ };
+          scenes below 8192 triangles when one frame is rendered at a time, else the wavefront pipeline; more samples: the wavefront pipeline */ };
 
 typedef struct {
     uint32_t struct_size;    /* = sizeof(vcrt_render_params) */

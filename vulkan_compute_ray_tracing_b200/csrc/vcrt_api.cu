@@ -454,9 +454,10 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     // (profiles/r02_v27_latency_*.log).
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch && !(p.flags & VCRT_FLAG_WAVEFRONT) && a.sample_count == 1u) {
         const bool deep = a.env.max_bounces > 4u;
-        // one deep frame at a time: the megakernel (no barrier between bounces) on small scenes, the wavefront pipeline on large ones, where
-        // the tail loop of its trace kernel has closed the gap (C3: 1.74 vs 1.80 ms per frame; bundled scene: 0.97 vs 0.84)
-        const bool wavefront = deep && ((fs && c->frames_n >= 2) || s.ntris >= 65536u);
+        // one deep frame at a time: the megakernel (no barrier between bounces) on very small scenes, the wavefront pipeline otherwise --
+        // the tail loop of its trace kernel has closed the gap (1080p, depth 8, ms per frame, wavefront vs megakernel: bundled scene of 1.4 K
+        // triangles 0.97 vs 0.84; lit box of 20 K 1.22 vs 1.29, 100 K 1.38 vs 1.56, 300 K 1.50 vs 1.61, 1 M 1.70 vs 1.80)
+        const bool wavefront = deep && ((fs && c->frames_n >= 2) || s.ntris >= 8192u);
         if (!wavefront) {
             a.flags |= deep ? VCRT_FLAG_MEGAKERNEL : VCRT_FLAG_STATIC_KERNEL;
             one_launch = true;
