@@ -1095,3 +1095,29 @@ def test_frames_in_flight_tile_shard_and_coverage(doge, family):
     assert same_bits(frames["sync"][1], frames["in_flight"][1]) and same_bits(frames["sync"][2], frames["in_flight"][2])
     covered = frames["sync"][1][..., 3] > 0
     assert 0 < covered.sum() < w * h / 2      # a third of the tiles, minus the uncovered border
+
+
+@pytest.mark.parametrize("family,nslots", [("wavefront", 4), ("mega", 2), ("auto", 3)])
+def test_frames_in_flight_long_run_equals_one_render(doge, family, nslots):
+    """300 progressive 1-spp frames in flight leave exactly the f32 accumulation that ONE 300-spp render leaves (samples folded in
+    sample order in both): the frame-order chain of the folds holds under sustained overlap, and the trace kernel's tail loop -- which
+    most of every small launch runs in -- never changes a hit."""
+    import vulkan_compute_ray_tracing_b200 as vcrt
+    from gpuharness import GpuScene
+    w, h, n = 320, 240, 300
+    flags = {"wavefront": vcrt.FLAG_WAVEFRONT, "mega": vcrt.FLAG_MEGAKERNEL, "auto": 0}[family]
+    kw = dict(shader="full", traversal="fast", rng="philox", accum="f32", trig="libm", max_bounces=8, philox_seed=11)
+    g = GpuScene(doge, w, h)
+    g.set_camera(CAM, 0)
+    g.material.clearAccum()
+    g.model.renderCommand(None, 0, vcrt.render_params(**kw, sample_begin=0, sample_count=n, flags=vcrt.FLAG_WAVEFRONT))
+    want = g.material.readAccumF32()
+    g.material.clearAccum()
+    g.material.framesBegin(nslots)
+    for k in range(n):
+        g.material.frameSubmit(vcrt.render_params(**kw, sample_begin=k, sample_count=1, flags=flags), total_samples=k + 1)
+    g.material.framesEnd()
+    got = g.material.readAccumF32()
+    assert same_bits(got, want), family
+    assert float(got[..., 3].min()) == n
+    g.close()
