@@ -40,6 +40,9 @@
 #ifndef VCRT_TAIL_SPLIT
 #define VCRT_TAIL_SPLIT 1  /* trace kernel: once the queue is dry, idle lanes of a warp take subtrees off the stacks of its busy lanes (vcrt_wavefront.cuh) */
 #endif
+#ifndef VCRT_TAIL_ENTER
+#define VCRT_TAIL_ENTER 16  /* ... the tail loop takes over once fewer than this many lanes of the warp are still walking (33 = as soon as the queue is dry).  33 / 28 / 24 / 16: C3 at 1 spp 2581 / 2578 / 2576 / 2629 Mrays/s, 8 and 64 spp unchanged (profiles/r02_v46_ab_tail_enter.log) */
+#endif
 #ifndef VCRT_TAIL_EXCHANGE
 #define VCRT_TAIL_EXCHANGE 0  /* ... owners and helpers exchange their closest hits at every round of reports, not only at the end: the loop over all helpers costs more than the culling returns -- C3 at 1 / 2 / 8 spp 2584 -> 2444, 3764 -> 3600, 5611 -> 5525 Mrays/s (profiles/r02_v37_ab_tail_exchange.log) */
 #endif

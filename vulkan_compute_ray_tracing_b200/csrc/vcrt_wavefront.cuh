@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(VCRT_PBLOCK, VCRT_PMINB) wf_trace_kernel(const
             }
         }
 #if VCRT_TAIL_SPLIT
-        if (__any_sync(FULL, done)) break;   // the queue has run dry: the rays still in flight are finished by the tail loop below
+        // the queue has run dry: the rays still in flight are finished by the tail loop below -- once fewer than VCRT_TAIL_ENTER lanes are
+        // still walking (with most lanes busy the phase schedule of this loop is the better one, and there is nobody to share with)
+        if (__any_sync(FULL, done) && __popc(__ballot_sync(FULL, t.node != EMPTY || pending != EMPTY)) < VCRT_TAIL_ENTER) break;
 #else
         if (__all_sync(FULL, done)) break;
 #endif
