@@ -212,7 +212,8 @@ int vcrt_reset_counters(vcrt_ctx* ctx);
  *                VCRT_ACCUM_F32: the f32 sum, which restarts when params->sample_begin == 0 (as the running mean does: its weight
  *                of the history is 0 at sample 0, ray-trace-compute.comp:375-379) and is resolved with 1/total_samples
  *                (0 = sample_begin + 1) and `gamma` as by vcrt_resolve
- *   host_dst     W*H*4 bytes or NULL (no read-back); valid after vcrt_frame_wait(slot) -- the vkWaitForFences of that slot
+ *   host_dst     W*H*4 bytes or NULL (no read-back); valid after vcrt_frame_wait(slot) -- the vkWaitForFences of that slot -- and
+ *                not to be freed or reused before that (the copy into it is asynchronous)
  * While frames are in flight the other calls that touch the context's images or buffers fail with VCRT_ERR_STATE; vcrt_set_ubo,
  * vcrt_set_option (thresholds), vcrt_get_info and vcrt_last_error are fine.  After vcrt_frames_end the target, the accumulation and
  * the counters are those of the last frame, as if the frames had been rendered synchronously.

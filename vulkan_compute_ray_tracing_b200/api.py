@@ -309,7 +309,8 @@ class ComputeMaterial:
 
     def frameSubmit(self, params, total_samples=0, gamma=0.0, out=None, currentFrame=0):
         """One 1-spp frame on the next slot: render, fold into the accumulation in frame order, resolve, read back into `out`
-        (a PinnedFrame or a (H, W, 4) uint8 array; None = no read-back).  Returns the slot; `out` is valid after frameWait(slot).
+        (a PinnedFrame or a (H, W, 4) uint8 array; None = no read-back).  Returns the slot; `out` is valid after frameWait(slot) and
+        must be kept alive by the caller until then (the copy into it is asynchronous).
         The UBO is buffers[currentFrame] of the uniform bundle, as in bind()."""
         self._require()
         if params.shader == 0 and self.m_computeShaderPath.split("/")[-1].split(".")[0] == "ray-trace-compute-simple":
