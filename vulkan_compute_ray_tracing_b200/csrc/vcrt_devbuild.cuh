@@ -27,7 +27,9 @@ namespace vcrt {
 namespace devbuild {
 
 #define VCRT_DB_EMPTY ((int32_t)0x80000000)
-#define VCRT_PLOC_RADIUS 8
+#ifndef VCRT_PLOC_RADIUS
+#define VCRT_PLOC_RADIUS 4   /* clusters look this far to either side for their nearest neighbour.  4-wide visits / triangle tests per ray on the host emulation (480x270, depth 8), radius 2 | 4 | 8 | 16, host SAH tree last: 1 M-triangle box 12.00/3.05 | 12.12/3.07 | 12.53/3.13 | 12.60/3.13 | 11.73/3.11; 100 K box 10.24/2.90 | 10.12/2.92 | 10.46/2.99 | - | 9.78/3.09; random 20 K-triangle soup 41.85/20.55 | 39.30/20.10 | 38.95/20.04 | - | 39.72/19.85 */
+#endif
 
 // ---- atomics that degrade to plain operations in the sequential host emulation
 VCRT_HD uint32_t atom_add(uint32_t* p, uint32_t v) {
