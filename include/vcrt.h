@@ -174,7 +174,8 @@ int vcrt_pack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile_c
 int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile_count, const void* packed_dev, size_t bytes);
 
 /* Tunables that do not change results.  "fast_bvh": "sah" (default; the fast traversal walks a surface-area-heuristic
- * tree built over the leaves of the bound bvh[]) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
+ * tree built over the leaves of the bound bvh[], optimised by reinsertion for scenes up to 2 Mi triangles), "sah_plain" (the same tree
+ * as built, a tenth of the host time) or "topology" (it keeps the bound tree's own topology); "fast_nodes": "auto"
  * (default: 4-wide quantised 64-byte nodes when the scene extent allows, else binary 64-byte float nodes), "q15x4" (4-wide quantised
  * whatever the extent), "q15" (binary quantised 32-byte nodes), "f32"; "fast_build": where the records are built -- "auto" (default: on the
  * device, by CUDA kernels reading the bound buffers where they lie, whenever the default tree is wanted (fast_bvh=sah with fast_nodes=auto|q15x4)

@@ -146,7 +146,8 @@ extern "C" int hostemu_render(const void* tris, uint32_t ntris, const void* mats
             if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
             return -1;
         }
-        if ((!(p->_reserved & 1u) && !rebuild_fast_bvh_sah(fb, e)) || !check_fast_depth(fb, e)) {   // test hook: _reserved bit 0 keeps the bound topology
+        // test hooks: _reserved bit 0 keeps the bound topology; bits 8..15 = reinsertion passes, bits 16..23 = percent of the nodes per pass
+        if ((!(p->_reserved & 1u) && (!rebuild_fast_bvh_sah(fb, e) || (((p->_reserved >> 8) & 255u) && !optimize_fast_bvh_reinsert(fb, (int)((p->_reserved >> 8) & 255u), 0.01f * (float)((p->_reserved >> 16) & 255u), e)))) || !check_fast_depth(fb, e)) {
             if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
             return -1;
         }

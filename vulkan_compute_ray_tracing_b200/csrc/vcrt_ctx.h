@@ -48,7 +48,8 @@ struct vcrt_ctx {
     bool fast_dirty = true;
     uint32_t continue_threshold = 20;   // option "continue_threshold" (33 - min(leaf, shade) leaves the schedule unchanged)
     uint32_t leaf_threshold = 6, shade_threshold = 8;   // persistent-kernel phase thresholds (options "leaf_threshold", "shade_threshold")
-    bool fast_sah = true;                 // option "fast_bvh": "sah" (rebuild the topology) | "topology" (keep the bound tree's)
+    bool fast_sah = true;                 // option "fast_bvh": "sah" | "sah_plain" (rebuild the topology) | "topology" (keep the bound tree's)
+    bool fast_reinsert = true;            // "sah": the rebuilt tree is optimised by reinsertion (vcrt_repack.cpp); "sah_plain": left as built
     int fast_nodes = 0;                   // option "fast_nodes": 0 "auto" (4-wide quantised when the scene extent allows) | 1 "q15" (binary) | 2 "f32" | 3 "q15x4"
     bool quantized = false, wide = false;
     int32_t froot4 = (int32_t)0x80000000;

@@ -214,6 +214,135 @@ bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err) {
     return true;
 }
 
+// ------------------------------------------------------------------------------------------ insertion-based optimisation
+// After Bittner, Hapala, Havran: "Fast insertion-based optimization of bounding volume hierarchies" (2013).  The top-down build fixes
+// the upper levels before it knows what lies below them; here inner nodes are taken out again, largest surface area first, and their
+// two children are put back where they increase the tree's total surface area least (branch-and-bound search from the root).  Leaves
+// keep their slots, so results cannot change; only the number of boxes a ray enters does.  Sequential (the tree is mutated in place).
+namespace {
+struct Reinserter {
+    uint32_t nleaf = 0, ninner = 0;
+    std::vector<Box> box;                 // node ids: inner 0 .. ninner-1, leaf ninner + slot
+    std::vector<int32_t> parent;
+    std::vector<int32_t> kid;             // 2 per inner node
+    int32_t root = 0;
+    static float area(const Box& b) { return b.half_area(); }
+    static Box merge(const Box& a, const Box& b) { Box r = a; r.grow(b); return r; }
+    bool inner(int32_t v) const { return (uint32_t)v < ninner; }
+    void refit(int32_t v) {
+        while (v >= 0) {
+            const Box nb = merge(box[kid[2 * v]], box[kid[2 * v + 1]]);
+            if (std::memcmp(&nb, &box[v], sizeof nb) == 0) break;
+            box[v] = nb;
+            v = parent[v];
+        }
+    }
+    struct Cand { float ind; int32_t node; bool operator<(const Cand& o) const { return ind > o.ind; } };
+    std::vector<Cand> heap;
+    int32_t find_place(const Box& b) {
+        const float ab = area(b);
+        float best_cost = std::numeric_limits<float>::infinity();
+        int32_t best = root;
+        heap.clear();
+        heap.push_back({0.0f, root});
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end());
+            const Cand c = heap.back();
+            heap.pop_back();
+            if (c.ind + ab >= best_cost) break;
+            const float direct = area(merge(box[c.node], b));
+            const float total = c.ind + direct;
+            if (total < best_cost) { best_cost = total; best = c.node; }
+            const float ci = total - area(box[c.node]);
+            if (inner(c.node) && ci + ab < best_cost) {
+                heap.push_back({ci, kid[2 * c.node]}); std::push_heap(heap.begin(), heap.end());
+                heap.push_back({ci, kid[2 * c.node + 1]}); std::push_heap(heap.begin(), heap.end());
+            }
+        }
+        return best;
+    }
+    void insert(int32_t v, int32_t at, int32_t fresh) {   // `fresh` (a free inner node) becomes the parent of `at` and `v`
+        const int32_t g = parent[at];
+        kid[2 * fresh] = at; kid[2 * fresh + 1] = v;
+        parent[at] = fresh; parent[v] = fresh; parent[fresh] = g;
+        box[fresh] = merge(box[at], box[v]);
+        if (g < 0) root = fresh;
+        else { kid[2 * g + (kid[2 * g] == at ? 0 : 1)] = fresh; refit(g); }
+    }
+    bool reinsert(int32_t n) {
+        const int32_t p = parent[n];
+        if (!inner(n) || p < 0 || parent[p] < 0) return false;   // the root and its children stay
+        const int32_t g = parent[p], s = kid[2 * p] == n ? kid[2 * p + 1] : kid[2 * p];
+        int32_t l = kid[2 * n], r = kid[2 * n + 1];
+        kid[2 * g + (kid[2 * g] == p ? 0 : 1)] = s;
+        parent[s] = g;
+        refit(g);
+        if (area(box[l]) < area(box[r])) std::swap(l, r);
+        insert(l, find_place(box[l]), n);
+        insert(r, find_place(box[r]), p);
+        return true;
+    }
+};
+}  // namespace
+
+bool optimize_fast_bvh_reinsert(FastBvh& fb, int passes, float fraction, std::string& err) {
+    const uint32_t n = fb.num_slots();
+    if (n < 8 || fb.root != 0 || fb.num_nodes() != n - 1) return true;   // nothing worth doing / not a tree built by rebuild_fast_bvh_sah
+    static const int kMin[2][3] = {{0, 2, 8}, {4, 6, 10}};
+    Reinserter t;
+    t.nleaf = n; t.ninner = n - 1;
+    t.box.resize(2 * (size_t)n - 1); t.parent.assign(2 * (size_t)n - 1, -1); t.kid.resize(2 * (size_t)(n - 1));
+    for (uint32_t i = 0; i < n - 1; ++i) {
+        const float* p = &fb.nodes[(size_t)i * 16];
+        for (int c = 0; c < 2; ++c) {
+            int32_t code; std::memcpy(&code, &p[12 + c], 4);
+            if (code == (int32_t)0x80000000) return true;              // not a full binary tree: leave it
+            const int32_t id = code >= 0 ? code : (int32_t)(t.ninner + (uint32_t)(~code));
+            if ((uint32_t)id >= t.box.size() || t.parent[id] >= 0) { err = "reinsertion: malformed tree"; return false; }
+            t.kid[2 * i + c] = id; t.parent[id] = (int32_t)i;
+            for (int a = 0; a < 3; ++a) { t.box[id].lo[a] = p[kMin[c][a]]; t.box[id].hi[a] = p[kMin[c][a] + 1]; }
+        }
+    }
+    t.parent[0] = -1;
+    t.box[0] = Reinserter::merge(t.box[t.kid[0]], t.box[t.kid[1]]);
+    t.root = 0;
+    std::vector<int32_t> order(t.ninner);
+    const uint32_t per_pass = std::max(1u, (uint32_t)((double)t.ninner * fraction));
+    for (int pass = 0; pass < passes; ++pass) {
+        for (uint32_t i = 0; i < t.ninner; ++i) order[i] = (int32_t)i;
+        std::partial_sort(order.begin(), order.begin() + std::min<size_t>(per_pass, order.size()), order.end(),
+                          [&](int32_t a, int32_t b) { return Reinserter::area(t.box[a]) > Reinserter::area(t.box[b]); });
+        for (uint32_t i = 0; i < per_pass && i < t.ninner; ++i) t.reinsert(order[i]);
+    }
+    // depth of the new tree; a tree the traversal stack could not hold is not taken
+    std::vector<float> nodes((size_t)(n - 1) * 16, 0.0f);
+    std::vector<int32_t> newid(t.ninner, -1);
+    struct Item { int32_t v; uint32_t depth; };
+    std::vector<Item> st;
+    uint32_t next = 0, max_depth = 0;
+    st.push_back({t.root, 0u});
+    newid[t.root] = (int32_t)next++;
+    while (!st.empty()) {
+        const Item it = st.back();
+        st.pop_back();
+        float* p = &nodes[(size_t)newid[it.v] * 16];
+        for (int c = 0; c < 2; ++c) {
+            const int32_t k = t.kid[2 * it.v + c];
+            int32_t code;
+            if (t.inner(k)) { newid[k] = (int32_t)next++; code = newid[k]; st.push_back({k, it.depth + 1}); }
+            else { code = ~(int32_t)((uint32_t)k - t.ninner); if (it.depth + 1 > max_depth) max_depth = it.depth + 1; }
+            for (int a = 0; a < 3; ++a) { p[kMin[c][a]] = t.box[k].lo[a]; p[kMin[c][a] + 1] = t.box[k].hi[a]; }
+            std::memcpy(&p[12 + c], &code, 4);
+        }
+    }
+    if (next != t.ninner) { err = "reinsertion: lost nodes"; return false; }
+    if (max_depth + 3 > 48) return true;   // too deep for the binary traversal stack: keep the tree as built
+    fb.nodes.swap(nodes);
+    fb.root = 0;
+    fb.depth = max_depth;
+    return true;
+}
+
 void precompute_triangles(FastBvh& fb) {
     const uint32_t n = fb.num_slots();
     fb.tris64.assign((size_t)n * 16, 0.0f);

@@ -38,6 +38,10 @@ bool check_fast_depth(const FastBvh& fb, std::string& err);
 // visits does).  The reference's builder splits at the median of a random axis (Bvh.h:160,175), which costs several
 // times more node visits per ray than a surface-area-heuristic tree.  Parallel over subtrees (OpenMP tasks).
 bool rebuild_fast_bvh_sah(FastBvh& fb, std::string& err);
+// Insertion-based optimisation of the tree rebuild_fast_bvh_sah made (Bittner et al. 2013): `passes` times, the `fraction` of the inner
+// nodes with the largest surface area is taken out and their children are put back where the tree's total surface area grows least.
+// Leaves keep their slots: results do not change.  A result too deep for the traversal stack is discarded (the tree stays as built).
+bool optimize_fast_bvh_reinsert(FastBvh& fb, int passes, float fraction, std::string& err);
 
 // 32-byte form of the inner nodes: the twelve child-box bounds as 15-bit fixed point in one scene-wide frame, rounded
 // outwards (boxes only grow, so culling stays conservative and results do not change), followed by the two child codes:
