@@ -218,3 +218,32 @@ def test_node_formats_give_identical_results(oracle, hostemu, doge, fmt):
         assert b["nodes"] >= f["nodes"]
         if fmt != "f32" and sc is doge:
             assert b["nodes"] <= 1.1 * f["nodes"]        # quantisation costs only a few per cent more visits here
+
+
+@pytest.mark.parametrize("passes,percent", [(1, 10), (3, 10), (4, 50)])
+def test_reinsertion_optimised_tree(oracle, hostemu, passes, percent):
+    """optimize_fast_bvh_reinsert (Bittner et al. 2013) moves subtrees about; leaves keep their slots, so every bit of the result must
+    stay what the reference traversal gives -- on random scenes with duplicated triangles (ties), on the awkward sizes, and with fewer
+    node visits than the tree as built on a scene large enough to have something to optimise."""
+    cam = (0.0, 6.0, 1.5)
+    for seed, n in ((21, 8), (22, 9), (23, 40), (24, 700), (25, 6000)):
+        sc = small_scene(n_tris=n, seed=seed)
+        kw = dict(shader="full", max_bounces=6, sample_count=2, accum="f32", rng="philox", stack_depth=64)
+        a = oracle.render(sc, cam, 80, 56, make_params(traversal="reference", **kw), want_aov=True)
+        for wide in (0, 8):
+            p = make_params(traversal="fast", **kw)
+            p._reserved = wide | (passes << 8) | (percent << 16)
+            b = hostemu.render(sc, cam, 80, 56, p, want_aov=True)
+            assert same_bits(a["accumf"], b["accumf"]) and same_bits(a["aov"], b["aov"]), (seed, n, wide)
+            assert a["counters"].rays == b["rays"]
+    if (passes, percent) == (3, 10):
+        from vulkan_compute_ray_tracing_b200 import scenegen
+        sc = scenegen.generate_box_scene(60000, seed=5)
+        kw = dict(shader="full", max_bounces=4, sample_count=1, accum="f32", rng="philox", stack_depth=64)
+        nodes = []
+        for res in (8, 8 | (3 << 8) | (10 << 16)):
+            p = make_params(traversal="fast", **kw)
+            p._reserved = res
+            r = hostemu.render(sc, (1.8, 8.6, 1.1), 160, 90, p)
+            nodes.append(r["nodes"] / r["rays"])
+        assert nodes[1] < nodes[0]

@@ -245,7 +245,8 @@ struct Reinserter {
         int32_t best = root;
         heap.clear();
         heap.push_back({0.0f, root});
-        while (!heap.empty()) {
+        int budget = 4096;   // degenerate scenes (thousands of coincident boxes) would otherwise search the whole tree for every node
+        while (!heap.empty() && budget-- > 0) {
             std::pop_heap(heap.begin(), heap.end());
             const Cand c = heap.back();
             heap.pop_back();
