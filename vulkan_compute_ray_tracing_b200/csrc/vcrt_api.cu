@@ -350,17 +350,26 @@ static int prepare_fast(vcrt_ctx* c) {
         if (ok && c->fast_sah) ok = rebuild_fast_bvh_sah(fb, c->fast_err);
         // insertion-based optimisation of the rebuilt tree (3 passes over the 10 % of the inner nodes with the largest area): 5 % fewer
         // node visits per ray for 3 s of host time per million triangles; scenes beyond 2 Mi triangles keep the tree as built
-        if (ok && c->fast_sah && c->fast_reinsert && fb.num_slots() <= (2u << 20)) ok = optimize_fast_bvh_reinsert(fb, 3, 0.10f, c->fast_err);
+        std::vector<float> plain_nodes;      // the tree as built, in case the optimised one cannot be walked as a 4-wide tree (its stack bound)
+        uint32_t plain_depth = 0;
+        const bool reinsert = ok && c->fast_sah && c->fast_reinsert && fb.num_slots() <= (2u << 20);
+        if (reinsert) { plain_nodes = fb.nodes; plain_depth = fb.depth; ok = optimize_fast_bvh_reinsert(fb, 3, 0.10f, c->fast_err); }
         if (ok) ok = check_fast_depth(fb, c->fast_err);   // the tree that will be walked: a deep bound tree is fine once rebuilt
         if (!ok) { c->fast_dirty = false; return fail(c, VCRT_ERR_INVALID, "fast traversal unavailable: " + c->fast_err); }   // a property of the bound tree: no retry
         precompute_triangles(fb);
+        // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
+        const float max_quantum = (c->fast_nodes == 1 || c->fast_nodes == 3) ? 3.0e38f : 2.5e-4f;
+        bool quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, max_quantum);
+        // 4-wide form of the quantised tree for the wavefront trace kernel ("auto" and "q15x4"; "q15" keeps the binary tree)
+        bool wide = quantized && c->fast_nodes != 1 && build_wide_bvh(fb, VCRT_FAST_STACK);
+        if (!wide && quantized && c->fast_nodes != 1 && reinsert) {   // the optimised tree asks for a deeper stack than the kernel has: walk the tree as built
+            fb.nodes.swap(plain_nodes); fb.depth = plain_depth;
+            quantized = quantize_fast_bvh(fb, max_quantum);
+            wide = quantized && build_wide_bvh(fb, VCRT_FAST_STACK);
+        }
         if ((rc = ensure(c, c->fnodes, fb.nodes.size() * 4, "allocate repacked nodes")) || (rc = ensure(c, c->ftris, fb.tris64.size() * 4, "allocate repacked triangles"))) return rc;
         if (!fb.nodes.empty()) CU(c, cudaMemcpyAsync(c->fnodes.ptr, fb.nodes.data(), fb.nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked nodes");
         if (!fb.tris64.empty()) CU(c, cudaMemcpyAsync(c->ftris.ptr, fb.tris64.data(), fb.tris64.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload repacked triangles");
-        // 32-byte quantised nodes: "auto" accepts quanta up to 2.5e-4 (the reference's own leaf padding is 1e-4), "q15" any
-        const bool quantized = c->fast_nodes != 2 && quantize_fast_bvh(fb, (c->fast_nodes == 1 || c->fast_nodes == 3) ? 3.0e38f : 2.5e-4f);
-        // 4-wide form of the quantised tree for the wavefront trace kernel ("auto" and "q15x4"; "q15" keeps the binary tree)
-        const bool wide = quantized && c->fast_nodes != 1 && build_wide_bvh(fb, VCRT_FAST_STACK);
         if (wide) {
             if ((rc = ensure(c, c->q4nodes, fb.q4nodes.size() * 4, "allocate 4-wide nodes"))) return rc;
             CU(c, cudaMemcpyAsync(c->q4nodes.ptr, fb.q4nodes.data(), fb.q4nodes.size() * 4, cudaMemcpyHostToDevice, c->stream), "upload 4-wide nodes");
