@@ -19,8 +19,11 @@ image (weak scaling) and the f32 accumulation buffers are summed onto rank 0 wit
             pinned host memory (scene resident, as after the reference's initScene); `with_scene_upload` also re-uploads the
             five scene buffers and rebuilds the traversal records every step.  Wall clock between synchronised barriers,
             max over ranks.
-  roofline  for the dominant kernel (wf_trace_kernel, timed per launch with CUDA events on its stream inside the timed
-            region).  C3's working set (21 MB of nodes + 64 MB of triangle records) is L2-resident on a B200, so HBM does not
+  roofline  for the dominant kernel (wf_trace_kernel, timed per launch with CUDA events on its stream).  When the timed region
+            runs as one pipeline those are the launches of the timed region; when it runs as two (wf_streams "auto", large
+            renders: one pipeline's shade launches overlap the other's trace launches) a launch's events also span the time it
+            shares the SMs, so the kernel is timed alone in `steps` further steps of the same workload with one pipeline, same
+            process, right after the timed region (`roofline.timed_as`, `roofline.timed_region`).  C3's working set (21 MB of nodes + 64 MB of triangle records) is L2-resident on a B200, so HBM does not
             bind it; what does is the rate at which L1TEX pulls divergent 32-byte sectors out of L2.  `peak` is that rate
             MEASURED IN THIS PROCESS before the timed region (tools/ubench/probe.cu: dependent random 32-byte LDG.256 gathers
             over a 32 MB L2-resident table, the kernel's own launch shape), `achieved` the kernel's own scene-record sector
@@ -433,7 +436,27 @@ def main():
     c, tot, max_ms = timed_steps(base, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     rays, kernel_ms, launches = int(c.rays), float(c.kernel_ms), int(c.launches)
-    trace_ms, trace_launches = float(c.trace_ms), int(c.trace_launches)
+    # ---- the dominant kernel timed ALONE.  A large render runs as two pipelines (option wf_streams, "auto"): one pipeline's shade
+    # launches overlap the other's trace launches, so inside the timed region the CUDA events around a trace launch also span the
+    # time it shares the SMs with other kernels.  The roofline figures come from `steps` more steps of the same workload, same
+    # process, L2 flushed likewise, with ONE pipeline -- every trace launch then has the GPU to itself -- right after the timed region.
+    pipelines = int(mat.getInfo("wf_pipelines") or 1)
+    if world > 1:       # every rank takes the same branch (tile shards can differ by one tile)
+        pl_ = torch.tensor([float(pipelines)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(pl_, op=dist.ReduceOp.MAX)
+        pipelines = int(pl_.item())
+    overlapped = None
+    c_roof, roof_ms = c, max_ms
+    if pipelines > 1:
+        user_streams = dict(kv.split("=", 1) for kv in args.option).get("wf_streams", "auto")
+        overlapped = {"pipelines": pipelines, "trace_ms_per_step_summed_over_overlapping_launches": float(c.trace_ms) / args.steps,
+                      "trace_launches_per_step": int(c.trace_launches) / args.steps}
+        mat.setOption("wf_streams", "1")
+        c_roof, _, roof_ms = timed_steps(base, args.steps, 1)
+        mat.setOption("wf_streams", user_streams)
+        step()      # queues back to the two-pipeline layout before anything else is timed
+        barrier()
+    trace_ms, trace_launches = float(c_roof.trace_ms), int(c_roof.trace_launches)
     total_rays, total_launches, total_trav, total_prim = tot[0], int(tot[1]), tot[2], tot[3]
     value = total_rays / (max_ms * 1e-3) / 1e6
 
@@ -662,12 +685,20 @@ def main():
         step_ms = max_ms / steps
         # the committed ncu DRAM capture applies to the headline shape only (C3 at its default size and sample count, per GPU)
         traffic_key = "c3" if (args.config == "c3" and (w, h, args.spp, args.triangles) == (1920, 1080, 64, 1000000) and args.scaling == "weak") else "none"
-        roof = kernel_accounting(mat, model, base.sample_count if world == 1 else max(base.sample_count // world, 1), c, steps, step_ms, probes, traffic_key, peak)
+        if pipelines > 1:
+            mat.setOption("wf_streams", "1")      # the counting step of the accounting: same launch shape as c_roof
+        roof = kernel_accounting(mat, model, base.sample_count if world == 1 else max(base.sample_count // world, 1), c_roof, steps, roof_ms / steps, probes, traffic_key, peak)
+        if pipelines > 1:
+            mat.setOption("wf_streams", user_streams)
+            if roof is not None:
+                roof["timed_as"] = ("the kernel alone: %d steps of the same workload with one pipeline (wf_streams=1, %.2f ms per step), in this process right after the "
+                                    "timed region; the timed region itself runs %d pipelines whose trace and shade launches overlap" % (steps, roof_ms / steps, pipelines))
+                roof["timed_region"] = overlapped
         if roof is None:      # A/B variants without a separate trace kernel
             roof = {"bound": "l2", "achieved": None, "peak": probes["l2_gather_gps"] * 32.0, "unit": "GB/s", "frac": None, "traffic": None, "kernel": "render kernel (one launch)"}
         bray, bray_info = oracle_bray(scene, w, h, args.bounces, tile_count=32)
         if trace_launches:
-            ach_c = bray * (rays / trace_launches) / (trace_ms * 1e-3 / trace_launches) / 1e9
+            ach_c = bray * (int(c_roof.rays) / trace_launches) / (trace_ms * 1e-3 / trace_launches) / 1e9
             roof["canonical"] = {"bytes_per_ray": bray, "achieved": ach_c, "peak": peak, "unit": "GB/s", "frac": ach_c / peak, "peak_source": peak_src,
                                  "note": "SURVEY 8d's figure, kept for the record: 48 B x fetches of the reference-order t-culled traversal of the bound median-split tree, per "
                                          "closest-hit query; the kernel walks its own 4-wide SAH tree (and bounce 0 once per pixel), so this is not a ceiling", **bray_info}

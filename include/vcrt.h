@@ -182,9 +182,11 @@ int vcrt_unpack_tiles(vcrt_ctx* ctx, int what, uint32_t tile_rank, uint32_t tile
  * and the scene allows; else by the host builder), "host", "device" (fail instead of falling back); "dispatch_traversal": what vcrt_dispatch walks -- "auto" (default: the fast tree whenever
  * the bound tree is at most 13 levels deep, i.e. whenever the shader's 16-entry stack cannot overflow; identical frames), "reference" (always the
  * literal hit_bvh), "fast"; "wf_batch_paths":
- *  paths per wavefront batch (queue memory: 120 B per path); "wf_streams": "auto" (default, = 1) or 1..4 -- the render is cut
- * into that many batches, run as parallel pipelines on separate streams with their own queue sets (an A/B knob: measured
- * slower than one pipeline on a 1-spp frame); "trace_timing": "auto" (default: multi-sample renders only) | "on" | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
+ *  paths per wavefront batch (queue memory: 120 B per path); "wf_streams": "auto" (default) or 1..4 -- the render is cut
+ * into that many batches, run as parallel pipelines on separate streams with their own queue sets, which share the queue memory of one
+ * batch; "auto" = 2 for calls of 32 Mi paths or more (one pipeline's shade launches overlap the other's trace launches: 3-5 % faster
+ * on a 64-spp 1080p frame), else 1 (slower than one pipeline on small frames); frames in flight run one pipeline each;
+ * vcrt_get_info "wf_pipelines" = what the last render used; "trace_timing": "auto" (default: multi-sample renders only) | "on" | "off" -- CUDA events around every trace launch (vcrt_counters.trace_ms);
  * "leaf_threshold" / "shade_threshold" / "continue_threshold": lanes (1..32); "host_threads": OpenMP threads of the host-side record build. */
 int vcrt_set_option(vcrt_ctx* ctx, const char* key, const char* value);
 

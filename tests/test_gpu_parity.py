@@ -347,6 +347,26 @@ def test_wavefront_pipelines_and_counters(gpu_doge, oracle, doge):
         assert c.primary_rays == 800 * 600 * 4 and c.traversals == c.rays - 800 * 600 * 3
     s = gpu_doge.render(CAM, traversal="fast", flags=8, **kw)["counters"]      # the one-launch kernel walks every query
     assert s.rays == c.rays and s.traversals == s.rays and s.primary_rays == c.primary_rays
+    gpu_doge.material.setOption("wf_streams", "auto")
+    # (3) "auto" runs calls of 32 Mi paths or more as two pipelines that share one batch's queue memory: same bits as one pipeline,
+    # also when the batches are small and alternate between the pipelines many times
+    from gpuharness import GpuScene
+    g = GpuScene(doge, 1920, 1080)
+    kw["sample_count"] = 17      # 1920 x 1056 covered pixels x 17 > 2^25
+    one = None
+    for streams, batch, pipelines in (("1", 256 << 20, 1), ("auto", 256 << 20, 2), ("auto", 3 << 20, 2), ("3", 5 << 20, 3)):
+        g.material.setOption("wf_streams", streams)
+        g.material.setOption("wf_batch_paths", str(batch))
+        b = g.render(CAM, traversal="fast", **kw)
+        assert int(g.material.getInfo("wf_pipelines")) == pipelines, (streams, batch)
+        one = one or b
+        assert same_bits(one["accumf"], b["accumf"]) and one["counters"].rays == b["counters"].rays, (streams, batch)
+    kw["sample_count"] = 4
+    g.material.setOption("wf_batch_paths", str(256 << 20))
+    g.material.setOption("wf_streams", "auto")
+    g.render(CAM, traversal="fast", **kw)
+    assert int(g.material.getInfo("wf_pipelines")) == 1      # a small call stays one pipeline
+    g.close()
 
 
 def test_c4_size_scene(oracle):

@@ -165,6 +165,7 @@ int vcrt_get_info(vcrt_ctx* c, const char* key, char* value, size_t capacity) {
         else if (k == "fast_build_stages") v = ok && c->built_on_device ? c->fast_build_stages : "";
         else { char b[32]; snprintf(b, sizeof b, "%.3f", c->fast_build_ms); v = b; }
     } else if (k == "wf_batch_paths") v = std::to_string(c->wf_batch);
+    else if (k == "wf_pipelines") v = std::to_string(c->wf_pipes_used);   // pipelines of the last wavefront render (option "wf_streams")
     else if (k == "dispatch_kernel") v = c->dispatch_fast ? "fast" : "reference";
     else if (k == "device") v = std::to_string(c->device);
     else return fail(c, VCRT_ERR_INVALID, "vcrt_get_info: unknown key '" + k + "'");
@@ -478,15 +479,18 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
     if (p.traversal == VCRT_TRAVERSAL_FAST && !one_launch) {
         // wavefront pipeline: a batch = a range of pixels x all samples of the call; queues sized for what the call needs, at most
         // wf_batch paths per batch.  Option "wf_streams" = n cuts the call into n batches that run as parallel pipelines on their
-        // own streams (each with its own queue set), so that the tail of one trace launch overlaps the others' work; "auto" = 1:
-        // measured on C3 (r02_v1), a 1-spp 1080p frame takes 2.19 ms as one pipeline and 2.41 ms as four -- every trace launch of a
+        // own streams (each with its own queue set), so that the tail of one trace launch overlaps the others' work.
+        // Measured on C3 (r02_v1): a 1-spp 1080p frame takes 2.19 ms as one pipeline and 2.41 ms as four -- every trace launch of a
         // small frame lasts as long as its longest ray (~0.2 ms) whatever its size, and four times as many launches cost more
-        // than the overlap returns.
+        // than the overlap returns.  A large render is another matter (r02_v55/56, C3): two pipelines overlap one's shade launches
+        // (ALU and streaming) with the other's trace launches (L2 gathers) -- 64 spp 40.0 -> 38.0 ms, 16 spp +1 %, 8 spp +-0, 4 spp
+        // -1.5 %; three or four are slower again.  "auto" = 2 from VCRT_WF_AUTO2_PATHS paths per call, else 1.
         const uint64_t need = (uint64_t)a.owned_tiles * 1024u * a.sample_count;
-        int sets = fs ? c->frames_n : c->wf_streams ? c->wf_streams : 1;   // frames in flight: one queue set per slot
+        int sets = fs ? c->frames_n : c->wf_streams ? c->wf_streams : need >= VCRT_WF_AUTO2_PATHS ? 2 : 1;   // frames in flight: one queue set per slot
         uint64_t per_set = fs ? need : (need + (uint64_t)sets - 1) / (uint64_t)sets;   // a frame in flight is one pipeline
         per_set = (per_set + a.sample_count - 1) / a.sample_count * a.sample_count;   // whole pixels
-        if (per_set > c->wf_batch) per_set = c->wf_batch;
+        const uint64_t cap = fs ? c->wf_batch : c->wf_batch / (uint64_t)sets;          // the pipelines share the queue memory of one batch
+        if (per_set > cap) per_set = cap / a.sample_count * a.sample_count;
         uint32_t want = (uint32_t)per_set;
         if (want < a.sample_count) want = a.sample_count;
         if (want < 1024u) want = 1024u;
@@ -511,6 +515,7 @@ static int render_common(vcrt_ctx* c, const vcrt_render_params& p, uint32_t covW
             return q;
         };
         pipes.n = fs ? 1 : sets;
+        c->wf_pipes_used = pipes.n;
         pipes.stream[0] = stream;
         if (fs) { pipes.q[0] = queue_set(fs_index); pipes.before_accumulate = c->last_folded; }
         for (int i = 0; i < (fs ? 0 : sets); ++i) {

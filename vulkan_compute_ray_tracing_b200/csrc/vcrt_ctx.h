@@ -66,6 +66,7 @@ struct vcrt_ctx {
     DevBuf wf_q0, wf_q1, wf_hit, wf_color, wf_counts;   // wavefront queues (all pipelines' sets, back to back)
     uint32_t wf_capacity = 0;              // paths per queue set
     int wf_sets = 0;                       // queue sets the buffers are currently carved into
+    int wf_pipes_used = 0;                 // info "wf_pipelines": what the last wavefront render ran as
     int wf_streams = 0;                    // option "wf_streams": 0 "auto" | 1..VCRT_MAX_PIPES pipelines of a wavefront render
     cudaStream_t pipe_stream[VCRT_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (the render stream)
     cudaEvent_t fork_ev = nullptr, join_ev[VCRT_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};

@@ -37,6 +37,10 @@
 #define VCRT_PREFETCH 0  /* trace kernel: 1 = prefetch the triangle of a postponed leaf into L1 (measured: 32 % SLOWER on C3, r01) */
 #endif
 
+#ifndef VCRT_WF_AUTO2_PATHS
+#define VCRT_WF_AUTO2_PATHS (1ull << 25)  /* wf_streams=auto: calls of this many paths or more run as two pipelines (vcrt_api.cu).  C3, 1 vs 2 pipelines: 4 spp 4945 / 4876, 8 spp 5725 / 5732, 16 spp (33.2 M paths) 6231 / 6286, 64 spp 6436-6651 / 6763-6765 Mrays/s (profiles/r02_v55_ab_pipelines.log) */
+#endif
+
 #ifndef VCRT_TAIL_SPLIT
 #define VCRT_TAIL_SPLIT 1  /* trace kernel: once the queue is dry, idle lanes of a warp take subtrees off the stacks of its busy lanes (vcrt_wavefront.cuh) */
 #endif
