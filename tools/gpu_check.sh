@@ -20,7 +20,7 @@ if [ "$2" != "quick" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-c4 > $out/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:wf_trace_kernel --launch-skip 8 -c 3 -o $out/trace_full -f python tools/sweep.py --spp 8 --reps 1 > $out/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:wf_trace_kernel --launch-skip 9 -c 2 -o $out/trace_c4 -f python tools/sweep.py --triangles 10000000 --spp 8 --reps 1 > $out/ncu_c4.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:wf_trace_kernel --csv --log-file $out/traffic.csv python tools/sweep.py --spp 64 --reps 0 > $out/traffic.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:wf_trace_kernel --csv --log-file $out/traffic_c4.csv python tools/sweep.py --triangles 10000000 --spp 8 --reps 0 > $out/traffic_c4.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:wf_trace_kernel --csv --log-file $out/traffic.csv python tools/sweep.py --spp 64 --reps 0 wf_streams=1 > $out/traffic.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:wf_trace_kernel --csv --log-file $out/traffic_c4.csv python tools/sweep.py --triangles 10000000 --spp 8 --reps 0 wf_streams=1 > $out/traffic_c4.log 2>&1
 fi
 ls -la $out
