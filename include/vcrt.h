@@ -99,7 +99,9 @@ typedef struct {
     uint64_t triangles;      /* triangle records fetched   (only with VCRT_FLAG_COUNT_TRAVERSAL) */
     double   kernel_ms;      /* device time of the render kernels (CUDA events) since the last reset */
     uint64_t launches;       /* kernels launched since the last reset */
-    double   trace_ms;       /* device time of the dominant kernel alone (wavefront trace launches; CUDA events per launch) */
+    double   trace_ms;       /* device time of the dominant kernel alone (wavefront trace launches; CUDA events per launch, summed).  With two or more
+                                pipelines ("wf_streams") the launches of different pipelines overlap and each one's events also span the time it shares
+                                the SMs: set wf_streams=1 to time the kernel by itself */
     uint64_t trace_launches; /* number of those launches */
     uint64_t traversals;     /* BVH traversals actually run.  The wavefront pipeline traces bounce 0 once per pixel and shares the hit
                                 among the pixel's samples (the shader's primary ray does not depend on the sample, :352-373), so
